@@ -1,0 +1,194 @@
+/* libfact_sm100.so -- C ABI of the B200-native FACT hot path (sm_100a).
+ *
+ * The reference (google-research/mint) has no FFI: its seam is the Python object contract between mint/ctl and
+ * the model.  Each entry point below names the reference computation it replaces (file:line
+ * relative to the reference tree).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer (no hidden allocation);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 or a negative FACT_ERR_*;
+ *    fact_last_error() returns a thread-local description of the last failure;
+ *  - activations are row-major fp32 [tokens, features]; "split" buffers are bf16 row-major, `hi` always present,
+ *    `lo` present only in FACT_MODE_PRECISE (x ~= hi + lo, see DESIGN.md "bf16x3");
+ *  - Keras weight layout is [in, out] row-major (y = x.W); packed GEMM weights are [out, in] bf16 (K-major);
+ *  - mode: FACT_MODE_PRECISE = bf16x3 split products, fp32 accumulate (meets the 1e-3 parity bar);
+ *          FACT_MODE_BF16    = single bf16 product (throughput mode, reported separately);
+ *          FACT_MODE_FP32_SIMT = CUDA-core fp32 GEMMs (debug cross-check only; attention core stays precise).
+ */
+#ifndef FACT_SM100_H_
+#define FACT_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FACT_OK 0
+#define FACT_ERR_BAD_SHAPE (-1)
+#define FACT_ERR_BAD_ALIGN (-2)
+#define FACT_ERR_CUDA (-3)
+#define FACT_ERR_WORKSPACE (-4)
+#define FACT_ERR_UNSUPPORTED (-5)
+
+#define FACT_MODE_PRECISE 0
+#define FACT_MODE_BF16 1
+#define FACT_MODE_FP32_SIMT 2
+
+#define FACT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FACT_API __attribute__((visibility("default")))
+#else
+#define FACT_API
+#endif
+
+FACT_API int fact_abi_version(void);
+FACT_API const char* fact_last_error(void);
+
+/* ---- weights -------------------------------------------------------------------------------------------- */
+
+/* One transformer layer = Residual(Norm(Attention)) + Residual(Norm(MLP)), base_models.py:102-106. */
+typedef struct fact_layer_weights {
+  const float* ln1_gamma;  /* [d]            base_models.py:27  */
+  const float* ln1_beta;   /* [d]                               */
+  const void* wqkv_hi;     /* bf16 [3d, d]   packed to_qkv kernel (no bias), base_models.py:68 */
+  const void* wqkv_lo;     /* bf16 [3d, d] or NULL (FACT_MODE_BF16) */
+  const void* wo_hi;       /* bf16 [d, d]    packed to_out kernel, base_models.py:69 */
+  const void* wo_lo;
+  const float* bo;         /* [d] */
+  const float* ln2_gamma;  /* [d] */
+  const float* ln2_beta;   /* [d] */
+  const void* w1_hi;       /* bf16 [ff, d]   packed MLP dense_0 kernel, base_models.py:51-52 */
+  const void* w1_lo;
+  const float* b1;         /* [ff] */
+  const void* w2_hi;       /* bf16 [d, ff]   packed MLP dense_1 kernel, base_models.py:53 */
+  const void* w2_lo;
+  const float* b2;         /* [d] */
+  /* Keras-layout fp32 kernels, only read in FACT_MODE_FP32_SIMT (may be NULL otherwise) */
+  const float* wqkv_f32;   /* [d, 3d] */
+  const float* wo_f32;     /* [d, d]  */
+  const float* w1_f32;     /* [d, ff] */
+  const float* w2_f32;     /* [ff, d] */
+} fact_layer_weights;
+
+typedef struct fact_dims {
+  int d_model;       /* 800  */
+  int n_heads;       /* 10   */
+  int d_ff;          /* 3072 */
+  int motion_layers; /* 2    */
+  int audio_layers;  /* 2    */
+  int cross_layers;  /* 12   */
+  int motion_seq;    /* 120  */
+  int audio_seq;     /* 240  */
+  int motion_dim;    /* 225  */
+  int audio_dim;     /* 35   */
+  int out_dim;       /* 225  */
+} fact_dims;
+
+/* All weights of FACTModel (fact_model.py:43-70). Layer arrays are host arrays of structs holding device pointers. */
+typedef struct fact_weights {
+  const fact_layer_weights* motion_layers; /* host array [motion_layers] */
+  const fact_layer_weights* audio_layers;  /* host array [audio_layers]  */
+  const fact_layer_weights* cross_layers;  /* host array [cross_layers]  */
+  const float* motion_embed_w;             /* [motion_dim, d] Keras layout (base_models.py:135) */
+  const float* motion_embed_b;             /* [d] */
+  const float* motion_pos;                 /* [motion_seq, d] (base_models.py:148-156) */
+  const float* audio_embed_w;              /* [audio_dim, d] */
+  const float* audio_embed_b;              /* [d] */
+  const float* audio_pos;                  /* [audio_seq, d] */
+  const float* out_w;                      /* [d, out_dim] Keras layout fp32 (base_models.py:176-180) */
+  const float* out_b;                      /* [out_dim] */
+  const void* out_w_hi;                    /* bf16 [out_dim, d] packed, for the all-rows head */
+  const void* out_w_lo;
+} fact_weights;
+
+/* Pack a Keras-layout fp32 kernel [k_in, n_out] into K-major bf16 [n_out, k_in]: hi = bf16(w), lo = bf16(w-hi).
+ * lo may be NULL. */
+FACT_API int fact_pack_weight(const float* w_keras, void* hi, void* lo, int k_in, int n_out, void* stream);
+
+/* ---- building-block kernels (each is also a unit-test seam) ---------------------------------------------- */
+
+/* Norm: y = LayerNorm(x; gamma, beta, eps=1e-5) (base_models.py:27-31), written as bf16 hi (+lo).
+ * gamma == NULL means "no normalisation": plain fp32 -> bf16 split of x. */
+FACT_API int fact_layernorm_split(const float* x, const float* gamma, const float* beta, void* y_hi, void* y_lo,
+                         int rows, int d, void* stream);
+
+/* Epilogues of fact_gemm */
+#define FACT_EPI_SPLIT 0           /* out_hi/lo = split(acc * (col < scale_cols ? scale : 1))            */
+#define FACT_EPI_BIAS_GELU_SPLIT 1 /* out_hi/lo = split(gelu_tanh(acc + bias))   (base_model_util.py:94) */
+#define FACT_EPI_BIAS_RESID_F32 2  /* out_f32[map(row)] = acc + bias + resid[row]                        */
+#define FACT_EPI_BIAS_F32 3        /* out_f32 = acc + bias                                               */
+
+typedef struct fact_gemm_epilogue {
+  int kind;           /* FACT_EPI_* */
+  float* out_f32;     /* [*, ldo] */
+  void* out_hi;       /* bf16 [*, ldo] */
+  void* out_lo;       /* bf16 or NULL */
+  int ldo;            /* output row pitch in elements */
+  const float* bias;  /* [n] or NULL */
+  const float* resid; /* [m, ldr] or NULL */
+  int ldr;
+  float scale;        /* FACT_EPI_SPLIT: multiplier of the first scale_cols columns (folds the attention scale) */
+  int scale_cols;
+  /* output-row remap for zero-copy concat (base_models.py:192-193): out_row = (row / seq_in) * seq_out + seq_off
+   * + row % seq_in ; seq_in == 0 disables it */
+  int seq_in, seq_out, seq_off;
+} fact_gemm_epilogue;
+
+/* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).
+ * a_hi/a_lo: bf16 [m, lda]; w_hi/w_lo: bf16 [n, ldw] (packed).  lo pointers NULL -> single bf16 product.
+ * Replaces the Keras Dense matmuls at base_models.py:51-53, 68-69, 176-180. */
+FACT_API int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+              int m, int n, int k, const fact_gemm_epilogue* epi, void* stream);
+
+/* fp32 CUDA-core GEMM, Keras-layout weight [k, n] (debug mode and the tiny embedding projections). Same epilogues. */
+FACT_API int fact_gemm_f32(const float* a, int lda, const float* w_keras, int m, int n, int k,
+                  const fact_gemm_epilogue* epi, void* stream);
+
+/* Attention core: softmax(q.k^T) . v per (batch, head), no mask (base_models.py:82-85).  qkv: bf16 [batch*n, 3d],
+ * column order (qkv, head, dh) (base_models.py:71-72); q must already carry scale*log2(e) (FACT_EPI_SPLIT scale).
+ * out: bf16 [batch*n, d], heads merged "b h n d -> b n (h d)" (base_models.py:73). */
+FACT_API int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
+              int head_dim, void* stream);
+
+/* LinearEmbedding + PositionEmbedding (fact_model.py:88-90,94-95; base_models.py:135,156):
+ * y[b*n_tok + t, :] = x[b, start + t, :f] . W[f, d] + bias + pos[t, :],  start = step_ptr ? *step_ptr : 0.
+ * x is [batch, x_len, f] with batch stride x_batch_stride elements. */
+FACT_API int fact_embed(const float* x, long long x_batch_stride, const int* step_ptr, const float* w, const float* bias,
+               const float* pos, float* y, int batch, int n_tok, int f, int d, void* stream);
+
+/* Output Dense on selected rows (base_models.py:200 + fact_model.py:128): for b < batch,
+ * out[b*out_batch_stride + (*step_ptr)*out_dim + j] = x[b*row_stride*d + :] . W[:, j] + bias[j]. */
+FACT_API int fact_head_rows(const float* x, long long row_stride, const float* w_keras, const float* bias, float* out,
+                   long long out_batch_stride, const int* step_ptr, int batch, int d, int out_dim, void* stream);
+
+/* MSE loss (fact_model.py:143-148): *loss = mean((target - pred[:, :t_len])^2); if dpred != NULL also writes
+ * dpred[B, n, out_dim] = dloss/dpred * loss_scale (zeros beyond t_len). partial: >= 1024 floats of scratch. */
+FACT_API int fact_mse(const float* target, const float* pred, float* loss, float* dpred, float* partial, int batch, int t_len,
+             int n, int out_dim, float loss_scale, void* stream);
+
+/* ---- whole-model entry points --------------------------------------------------------------------------- */
+
+FACT_API size_t fact_workspace_bytes(const fact_dims* dims, int batch, int mode);
+
+/* FACTModel.call (fact_model.py:72-101): motion [B, motion_seq, motion_dim], audio [B, audio_seq, audio_dim]
+ * -> out [B, motion_seq + audio_seq, out_dim]. */
+FACT_API int fact_forward(const fact_dims* dims, const fact_weights* w, const float* motion, const float* audio, float* out,
+                 int batch, void* workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* FACTModel.infer_auto_regressive (fact_model.py:103-132).
+ * motion_hist: [B, motion_seq + n_frames, motion_dim]; the first motion_seq rows hold the seed, frames are appended
+ * in place (the shift-by-one of fact_model.py:131 is an index offset into this buffer).
+ * audio: [B, audio_len, audio_dim].  n_frames must be <= min(steps, audio_len - audio_seq + 1) (the caller applies
+ * the early-stop rule of fact_model.py:125-126).  step_counter: device int scratch.
+ * use_graph != 0 replays one captured CUDA graph per frame. */
+FACT_API int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist, const float* audio,
+                               int audio_len, int batch, int n_frames, int* step_counter, void* workspace,
+                               size_t workspace_bytes, int mode, int use_graph, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACT_SM100_H_ */

@@ -1,0 +1,465 @@
+// Memory-bound kernels of the FACT hot path and the fp32 CUDA-core GEMM used for the tiny embedding
+// projections and as the debug cross-check of the tcgen05 path.
+//   layernorm_split : Norm (mint/core/base_models.py:22-31) fused with the fp32 -> bf16 hi/lo operand split
+//   pack_weight     : Keras [in,out] fp32 kernel -> K-major bf16 hi/lo [out,in]
+//   gemm_f32        : LinearEmbedding + PositionEmbedding (base_models.py:130-156) and debug GEMMs
+//   head_rows       : output Dense on one row per sample (base_models.py:200, fact_model.py:128)
+//   mse             : FACTModel.loss (fact_model.py:143-148)
+#include "fact_internal.h"
+#include "fact_ptx.cuh"
+
+namespace fact {
+
+// ------------------------------------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return FACT_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm + split
+// One warp per row, row kept in registers (d <= 1024, d % 4 == 0); two-pass mean / biased variance, eps 1e-5.
+template <bool NORM>
+__global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, bf16* __restrict__ hi,
+                                                       bf16* __restrict__ lo, int rows, int d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int nv = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    v[i] = idx < nv ? __ldg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (NORM) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / static_cast<float>(d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + i * 32 < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q / static_cast<float>(d) + 1e-5f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* hr = reinterpret_cast<uint2*>(hi + static_cast<size_t>(row) * d);
+  uint2* lr = lo ? reinterpret_cast<uint2*>(lo + static_cast<size_t>(row) * d) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      float4 y = v[i];
+      if (NORM) {
+        const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
+        y.x = (y.x - mean) * rstd * gg.x + bb.x;
+        y.y = (y.y - mean) * rstd * gg.y + bb.y;
+        y.z = (y.z - mean) * rstd * gg.z + bb.z;
+        y.w = (y.w - mean) * rstd * gg.w + bb.w;
+      }
+      bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(y.x, h0, l0);
+      split_bf16(y.y, h1, l1);
+      split_bf16(y.z, h2, l2);
+      split_bf16(y.w, h3, l3);
+      hr[idx] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      if (lr) lr[idx] = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- weight packing
+// w [k_in, n_out] fp32 row-major  ->  hi/lo [n_out, k_in] bf16 (transpose through a padded shared tile)
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ hi,
+                                                          bf16* __restrict__ lo, int k_in, int n_out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < k_in && n < n_out) ? w[static_cast<size_t>(k) * n_out + n] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (n < n_out && k < k_in) {
+      bf16 h, l;
+      split_bf16(tile[tx][r], h, l);
+      hi[static_cast<size_t>(n) * k_in + k] = h;
+      if (lo) lo[static_cast<size_t>(n) * k_in + k] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- fp32 SIMT GEMM
+struct SimtArgs {
+  // A operand: either fp32 (a_f32) or split bf16 (a_hi [+ a_lo]); row r lives at
+  //   base + (r / a_seq) * a_batch_stride + (start + r % a_seq) * lda      (a_seq == 0: base + r * lda)
+  const float* a_f32;
+  const bf16* a_hi;
+  const bf16* a_lo;
+  long long a_batch_stride;
+  int a_seq;
+  const int* step_ptr;
+  int lda;
+  const float* w;  // Keras layout [k, n]
+  int m, n, k;
+  // epilogue
+  int kind;
+  float* out_f32;
+  bf16* out_hi;
+  bf16* out_lo;
+  int ldo;
+  const float* bias;
+  const float* resid;
+  int ldr;
+  float scale;
+  int scale_cols;
+  int seq_in, seq_out, seq_off;
+  const float* pos;  // [pos_seq, n] added to row (r % pos_seq), or NULL
+  int pos_seq;
+};
+
+// 64 x 64 tile, 16-deep K slices, 256 threads x (4 x 4) outputs.
+__global__ void __launch_bounds__(256) gemm_f32_kernel(SimtArgs p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int start = p.step_ptr ? *p.step_ptr : 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < p.k; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, kk = e & 15;  // A: k fastest -> coalesced along the row
+      const int row = m0 + r, k = k0 + kk;
+      float a = 0.f;
+      if (row < p.m && k < p.k) {
+        const size_t off = p.a_seq ? static_cast<size_t>(row / p.a_seq) * p.a_batch_stride +
+                                         static_cast<size_t>(start + row % p.a_seq) * p.lda + k
+                                   : static_cast<size_t>(row) * p.lda + k;
+        if (p.a_f32) a = p.a_f32[off];
+        else a = __bfloat162float(p.a_hi[off]) + (p.a_lo ? __bfloat162float(p.a_lo[off]) : 0.f);
+      }
+      As[kk][r] = a;
+    }
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int kk = e >> 6, c = e & 63;
+      const int k = k0 + kk, col = n0 + c;
+      Ws[kk][c] = (k < p.k && col < p.n) ? p.w[static_cast<size_t>(k) * p.n + col] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= p.m) continue;
+    const int orow = p.seq_in ? (row / p.seq_in) * p.seq_out + p.seq_off + row % p.seq_in : row;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= p.n) continue;
+      float x = acc[i][j];
+      if (p.kind == FACT_EPI_SPLIT) {
+        if (col < p.scale_cols) x *= p.scale;
+      } else if (p.bias) {
+        x += p.bias[col];
+      }
+      if (p.pos) x += p.pos[static_cast<size_t>(row % p.pos_seq) * p.n + col];
+      if (p.kind == FACT_EPI_BIAS_GELU_SPLIT) x = gelu_tanh(x);
+      if (p.kind == FACT_EPI_BIAS_RESID_F32) x += p.resid[static_cast<size_t>(row) * p.ldr + col];
+      const size_t o = static_cast<size_t>(orow) * p.ldo + col;
+      if (p.kind == FACT_EPI_SPLIT || p.kind == FACT_EPI_BIAS_GELU_SPLIT) {
+        bf16 h, l;
+        split_bf16(x, h, l);
+        p.out_hi[o] = h;
+        if (p.out_lo) p.out_lo[o] = l;
+      } else {
+        p.out_f32[o] = x;
+      }
+    }
+  }
+}
+
+static int launch_simt(const SimtArgs& p, cudaStream_t st) {
+  dim3 grid((p.n + 63) / 64, (p.m + 63) / 64);
+  gemm_f32_kernel<<<grid, 256, 0, st>>>(p);
+  FACT_LAUNCH_CHECK("gemm_f32_kernel launch");
+  return FACT_OK;
+}
+
+static void fill_epi(SimtArgs& p, const fact_gemm_epilogue* e) {
+  p.kind = e->kind;
+  p.out_f32 = e->out_f32;
+  p.out_hi = static_cast<bf16*>(e->out_hi);
+  p.out_lo = static_cast<bf16*>(e->out_lo);
+  p.ldo = e->ldo;
+  p.bias = e->bias;
+  p.resid = e->resid;
+  p.ldr = e->ldr;
+  p.scale = e->scale;
+  p.scale_cols = e->scale_cols;
+  p.seq_in = e->seq_in;
+  p.seq_out = e->seq_out;
+  p.seq_off = e->seq_off;
+  p.pos = nullptr;
+  p.pos_seq = 1;
+}
+
+static int check_epi(const fact_gemm_epilogue* e) {
+  FACT_REQUIRE(e != nullptr, FACT_ERR_BAD_SHAPE, "null epilogue");
+  const bool split_out = e->kind == FACT_EPI_SPLIT || e->kind == FACT_EPI_BIAS_GELU_SPLIT;
+  FACT_REQUIRE(e->kind >= 0 && e->kind <= 3, FACT_ERR_UNSUPPORTED, "unknown epilogue kind %d", e->kind);
+  FACT_REQUIRE(split_out ? e->out_hi != nullptr : e->out_f32 != nullptr, FACT_ERR_BAD_SHAPE,
+               "epilogue output buffer missing");
+  FACT_REQUIRE(e->kind != FACT_EPI_BIAS_RESID_F32 || e->resid, FACT_ERR_BAD_SHAPE, "resid epilogue needs resid");
+  return FACT_OK;
+}
+
+// gemm on split-bf16 activations with the fp32 Keras-layout weight (FACT_MODE_FP32_SIMT); internal
+int gemm_simt_split(const void* a_hi, const void* a_lo, int lda, const float* w_keras, int m, int n, int k,
+                    const fact_gemm_epilogue* epi, cudaStream_t st) {
+  int rc = check_epi(epi);
+  if (rc) return rc;
+  FACT_REQUIRE(a_hi && w_keras, FACT_ERR_BAD_SHAPE, "gemm_simt_split: null operand (fp32 weights not provided?)");
+  SimtArgs p{};
+  p.a_hi = static_cast<const bf16*>(a_hi);
+  p.a_lo = static_cast<const bf16*>(a_lo);
+  p.lda = lda;
+  p.w = w_keras;
+  p.m = m;
+  p.n = n;
+  p.k = k;
+  fill_epi(p, epi);
+  return launch_simt(p, st);
+}
+
+// ------------------------------------------------------------------------------------------- head on one row / sample
+__global__ void __launch_bounds__(256) head_rows_kernel(const float* __restrict__ x, long long row_stride,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ out, long long out_batch_stride,
+                                                        const int* __restrict__ step_ptr, int d, int out_dim) {
+  extern __shared__ float xs[];
+  const int b = blockIdx.x;
+  const float* xr = x + static_cast<size_t>(b) * row_stride * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) xs[i] = xr[i];
+  __syncthreads();
+  const int step = step_ptr ? *step_ptr : 0;
+  for (int j = threadIdx.x; j < out_dim; j += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < d; ++k) acc = fmaf(xs[k], __ldg(w + static_cast<size_t>(k) * out_dim + j), acc);
+    out[static_cast<size_t>(b) * out_batch_stride + static_cast<size_t>(step) * out_dim + j] = acc + bias[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- MSE
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ target,
+                                                          const float* __restrict__ pred, float* __restrict__ partial,
+                                                          int batch, int t_len, int n, int od) {
+  const long long total = static_cast<long long>(batch) * t_len * od;
+  float s = 0.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int j = static_cast<int>(i % od);
+    const long long bt = i / od;
+    const int t = static_cast<int>(bt % t_len), b = static_cast<int>(bt / t_len);
+    const float df = target[i] - pred[(static_cast<size_t>(b) * n + t) * od + j];
+    s = fmaf(df, df, s);
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; ++i) tsum += red[i];
+    partial[blockIdx.x] = tsum;
+  }
+}
+__global__ void __launch_bounds__(256) mse_final_kernel(const float* __restrict__ partial, int nparts, float* loss,
+                                                        float inv_total) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; ++i) tsum += red[i];
+    *loss = tsum * inv_total;
+  }
+}
+__global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ target,
+                                                       const float* __restrict__ pred, float* __restrict__ dpred,
+                                                       int batch, int t_len, int n, int od, float coef) {
+  const long long total = static_cast<long long>(batch) * n * od;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int j = static_cast<int>(i % od);
+    const long long bt = i / od;
+    const int t = static_cast<int>(bt % n), b = static_cast<int>(bt / n);
+    dpred[i] = t < t_len ? coef * (pred[i] - target[(static_cast<size_t>(b) * t_len + t) * od + j]) : 0.f;
+  }
+}
+
+__global__ void step_set_kernel(int* p, int v) { *p = v; }
+__global__ void step_inc_kernel(int* p) { *p += 1; }
+
+int step_set(int* p, int v, cudaStream_t st) {
+  step_set_kernel<<<1, 1, 0, st>>>(p, v);
+  FACT_LAUNCH_CHECK("step_set_kernel");
+  return FACT_OK;
+}
+int step_inc(int* p, cudaStream_t st) {
+  step_inc_kernel<<<1, 1, 0, st>>>(p);
+  FACT_LAUNCH_CHECK("step_inc_kernel");
+  return FACT_OK;
+}
+
+}  // namespace fact
+
+using namespace fact;
+
+extern "C" int fact_abi_version(void) { return FACT_ABI_VERSION; }
+extern "C" const char* fact_last_error(void) { return g_err; }
+
+extern "C" int fact_layernorm_split(const float* x, const float* gamma, const float* beta, void* y_hi, void* y_lo,
+                                    int rows, int d, void* stream) {
+  FACT_REQUIRE(x && y_hi, FACT_ERR_BAD_SHAPE, "fact_layernorm_split: null buffer");
+  FACT_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 1024, FACT_ERR_BAD_SHAPE,
+               "fact_layernorm_split: need 0 < d <= 1024, d %% 4 == 0 (rows=%d d=%d)", rows, d);
+  FACT_REQUIRE((gamma == nullptr) == (beta == nullptr), FACT_ERR_BAD_SHAPE, "gamma and beta go together");
+  FACT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_hi) & 7) == 0,
+               FACT_ERR_BAD_ALIGN, "fact_layernorm_split: x must be 16-B, y 8-B aligned");
+  const int grid = (rows + 7) / 8;
+  cudaStream_t st = as_stream(stream);
+  if (gamma)
+    ln_split_kernel<true><<<grid, 256, 0, st>>>(x, gamma, beta, static_cast<bf16*>(y_hi), static_cast<bf16*>(y_lo),
+                                                rows, d);
+  else
+    ln_split_kernel<false><<<grid, 256, 0, st>>>(x, nullptr, nullptr, static_cast<bf16*>(y_hi),
+                                                 static_cast<bf16*>(y_lo), rows, d);
+  FACT_LAUNCH_CHECK("ln_split_kernel launch");
+  return FACT_OK;
+}
+
+extern "C" int fact_pack_weight(const float* w_keras, void* hi, void* lo, int k_in, int n_out, void* stream) {
+  FACT_REQUIRE(w_keras && hi && k_in > 0 && n_out > 0, FACT_ERR_BAD_SHAPE, "fact_pack_weight: bad arguments");
+  dim3 grid((n_out + 31) / 32, (k_in + 31) / 32);
+  pack_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_keras, static_cast<bf16*>(hi), static_cast<bf16*>(lo),
+                                                          k_in, n_out);
+  FACT_LAUNCH_CHECK("pack_weight_kernel launch");
+  return FACT_OK;
+}
+
+extern "C" int fact_gemm_f32(const float* a, int lda, const float* w_keras, int m, int n, int k,
+                             const fact_gemm_epilogue* epi, void* stream) {
+  int rc = check_epi(epi);
+  if (rc) return rc;
+  FACT_REQUIRE(a && w_keras && m > 0 && n > 0 && k > 0, FACT_ERR_BAD_SHAPE, "fact_gemm_f32: bad arguments");
+  SimtArgs p{};
+  p.a_f32 = a;
+  p.lda = lda;
+  p.w = w_keras;
+  p.m = m;
+  p.n = n;
+  p.k = k;
+  fill_epi(p, epi);
+  return launch_simt(p, as_stream(stream));
+}
+
+extern "C" int fact_embed(const float* x, long long x_batch_stride, const int* step_ptr, const float* w,
+                          const float* bias, const float* pos, float* y, int batch, int n_tok, int f, int d,
+                          void* stream) {
+  FACT_REQUIRE(x && w && bias && pos && y, FACT_ERR_BAD_SHAPE, "fact_embed: null buffer");
+  FACT_REQUIRE(batch > 0 && n_tok > 0 && f > 0 && d > 0, FACT_ERR_BAD_SHAPE, "fact_embed: bad shape");
+  SimtArgs p{};
+  p.a_f32 = x;
+  p.a_batch_stride = x_batch_stride;
+  p.a_seq = n_tok;
+  p.step_ptr = step_ptr;
+  p.lda = f;
+  p.w = w;
+  p.m = batch * n_tok;
+  p.n = d;
+  p.k = f;
+  p.kind = FACT_EPI_BIAS_F32;
+  p.out_f32 = y;
+  p.ldo = d;
+  p.bias = bias;
+  p.pos = pos;
+  p.pos_seq = n_tok;
+  return launch_simt(p, as_stream(stream));
+}
+
+extern "C" int fact_head_rows(const float* x, long long row_stride, const float* w_keras, const float* bias,
+                              float* out, long long out_batch_stride, const int* step_ptr, int batch, int d,
+                              int out_dim, void* stream) {
+  FACT_REQUIRE(x && w_keras && bias && out, FACT_ERR_BAD_SHAPE, "fact_head_rows: null buffer");
+  FACT_REQUIRE(batch > 0 && d > 0 && d <= 8192 && out_dim > 0, FACT_ERR_BAD_SHAPE, "fact_head_rows: bad shape");
+  head_rows_kernel<<<batch, 256, d * sizeof(float), as_stream(stream)>>>(x, row_stride, w_keras, bias, out,
+                                                                         out_batch_stride, step_ptr, d, out_dim);
+  FACT_LAUNCH_CHECK("head_rows_kernel launch");
+  return FACT_OK;
+}
+
+extern "C" int fact_mse(const float* target, const float* pred, float* loss, float* dpred, float* partial, int batch,
+                        int t_len, int n, int out_dim, float loss_scale, void* stream) {
+  FACT_REQUIRE(target && pred && loss && partial, FACT_ERR_BAD_SHAPE, "fact_mse: null buffer");
+  FACT_REQUIRE(batch > 0 && t_len > 0 && t_len <= n && out_dim > 0, FACT_ERR_BAD_SHAPE, "fact_mse: bad shape");
+  const long long total = static_cast<long long>(batch) * t_len * out_dim;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > 1024) grid = 1024;
+  cudaStream_t st = as_stream(stream);
+  mse_partial_kernel<<<grid, 256, 0, st>>>(target, pred, partial, batch, t_len, n, out_dim);
+  FACT_LAUNCH_CHECK("mse_partial_kernel launch");
+  mse_final_kernel<<<1, 256, 0, st>>>(partial, grid, loss, 1.0f / static_cast<float>(total));
+  FACT_LAUNCH_CHECK("mse_final_kernel launch");
+  if (dpred) {
+    const long long all = static_cast<long long>(batch) * n * out_dim;
+    int g2 = static_cast<int>((all + 255) / 256);
+    if (g2 > 4096) g2 = 4096;
+    mse_grad_kernel<<<g2, 256, 0, st>>>(target, pred, dpred, batch, t_len, n, out_dim,
+                                        2.0f * loss_scale / static_cast<float>(total));
+    FACT_LAUNCH_CHECK("mse_grad_kernel launch");
+  }
+  return FACT_OK;
+}

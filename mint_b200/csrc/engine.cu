@@ -1,0 +1,305 @@
+// Whole-model sequencing of the FACT hot path on one GPU (C++ runtime above the kernels):
+//   fact_forward                -- FACTModel.call                  (mint/core/fact_model.py:72-101)
+//   fact_infer_auto_regressive  -- FACTModel.infer_auto_regressive (mint/core/fact_model.py:103-132)
+// One transformer layer (base_models.py:102-106) is 7 launches:
+//   LN+split -> QKV GEMM (split epilogue, q pre-scaled) -> attention core -> out-proj GEMM (+bias +residual, in place)
+//   LN+split -> FF1 GEMM (+bias, GELU, split) -> FF2 GEMM (+bias +residual)
+// The last FF2 of each modality encoder writes straight into its slice of the [B, 360, d] cross-modal buffer
+// (the tf.concat of base_models.py:192-193 costs nothing).  The AR loop keeps a device-side step counter: the
+// shift-by-one of fact_model.py:131 and the audio window slice of :124 are row offsets read by the embedding
+// kernel, so one captured CUDA graph is replayed once per generated frame.
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "fact_internal.h"
+#include "fact_ptx.cuh"
+
+namespace fact {
+int gemm_simt_split(const void* a_hi, const void* a_lo, int lda, const float* w_keras, int m, int n, int k,
+                    const fact_gemm_epilogue* epi, cudaStream_t st);
+int step_set(int* p, int v, cudaStream_t st);
+int step_inc(int* p, cudaStream_t st);
+
+struct Workspace {
+  float *xm, *xa, *xc;
+  bf16 *ln_hi, *ln_lo, *ao_hi, *ao_lo, *qkv_hi, *qkv_lo, *h_hi, *h_lo;
+};
+
+static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
+
+static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Workspace* ws) {
+  const size_t d = dm->d_model, ff = dm->d_ff;
+  const size_t tm = static_cast<size_t>(batch) * dm->motion_seq, ta = static_cast<size_t>(batch) * dm->audio_seq;
+  const size_t tc = tm + ta;
+  const bool lo = mode != FACT_MODE_BF16;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return base ? static_cast<uint8_t*>(base) + o : nullptr;
+  };
+  Workspace w{};
+  w.xm = reinterpret_cast<float*>(take(tm * d * 4));
+  w.xa = reinterpret_cast<float*>(take(ta * d * 4));
+  w.xc = reinterpret_cast<float*>(take(tc * d * 4));
+  w.ln_hi = reinterpret_cast<bf16*>(take(tc * d * 2));
+  w.ln_lo = lo ? reinterpret_cast<bf16*>(take(tc * d * 2)) : nullptr;
+  w.ao_hi = reinterpret_cast<bf16*>(take(tc * d * 2));
+  w.ao_lo = lo ? reinterpret_cast<bf16*>(take(tc * d * 2)) : nullptr;
+  w.qkv_hi = reinterpret_cast<bf16*>(take(tc * 3 * d * 2));
+  w.qkv_lo = lo ? reinterpret_cast<bf16*>(take(tc * 3 * d * 2)) : nullptr;
+  w.h_hi = reinterpret_cast<bf16*>(take(tc * ff * 2));
+  w.h_lo = lo ? reinterpret_cast<bf16*>(take(tc * ff * 2)) : nullptr;
+  if (ws) *ws = w;
+  return off;
+}
+
+static int check_dims(const fact_dims* dm) {
+  FACT_REQUIRE(dm != nullptr, FACT_ERR_BAD_SHAPE, "null dims");
+  FACT_REQUIRE(dm->d_model > 0 && dm->n_heads > 0 && dm->d_model % dm->n_heads == 0, FACT_ERR_BAD_SHAPE,
+               "d_model %d not divisible by heads %d", dm->d_model, dm->n_heads);
+  FACT_REQUIRE(dm->d_model % 8 == 0 && dm->d_ff % 8 == 0, FACT_ERR_BAD_ALIGN,
+               "d_model and d_ff must be multiples of 8 (TMA 16-B row pitch)");
+  FACT_REQUIRE(dm->d_model <= 1024, FACT_ERR_UNSUPPORTED, "d_model > 1024 not supported by the LayerNorm kernel");
+  const int dh = dm->d_model / dm->n_heads;
+  FACT_REQUIRE(dh == 16 || dh == 32 || dh == 64 || dh == 80, FACT_ERR_UNSUPPORTED, "head_dim %d not instantiated", dh);
+  return FACT_OK;
+}
+
+// GEMM dispatch on mode
+static int dense(int mode, const bf16* a_hi, const bf16* a_lo, int lda, const void* w_hi, const void* w_lo,
+                 const float* w_f32, int m, int n, int k, const fact_gemm_epilogue* e, cudaStream_t st) {
+  if (mode == FACT_MODE_FP32_SIMT) return gemm_simt_split(a_hi, a_lo, lda, w_f32, m, n, k, e, st);
+  if (mode == FACT_MODE_PRECISE) {
+    FACT_REQUIRE(w_lo != nullptr, FACT_ERR_BAD_SHAPE, "precise mode needs the lo half of every packed weight");
+    return fact_gemm(a_hi, a_lo, lda, w_hi, w_lo, k, m, n, k, e, st);
+  }
+  return fact_gemm(a_hi, nullptr, lda, w_hi, nullptr, k, m, n, k, e, st);
+}
+
+// One transformer layer on x [tokens, d] (in place unless `dst` remaps the final residual write).
+static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x, int batch, int seq, int mode,
+                     const Workspace& ws, float* dst, int dst_seq, int dst_off, cudaStream_t st) {
+  const int d = dm->d_model, ff = dm->d_ff, H = dm->n_heads, dh = d / H;
+  const int M = batch * seq;
+  const bool lo = mode != FACT_MODE_BF16;
+  int rc;
+  // --- Residual(Norm(Attention))
+  if ((rc = fact_layernorm_split(x, L.ln1_gamma, L.ln1_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
+  fact_gemm_epilogue e{};
+  e.kind = FACT_EPI_SPLIT;
+  e.out_hi = ws.qkv_hi;
+  e.out_lo = lo ? ws.qkv_lo : nullptr;
+  e.ldo = 3 * d;
+  e.scale = static_cast<float>(1.0 / sqrt(static_cast<double>(d)) * 1.4426950408889634);  // d_model^-0.5 * log2(e)
+  e.scale_cols = d;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st))) return rc;
+  if ((rc = fact_sdpa(ws.qkv_hi, lo ? ws.qkv_lo : nullptr, ws.ao_hi, lo ? ws.ao_lo : nullptr, batch, seq, H, dh, st)))
+    return rc;
+  e = fact_gemm_epilogue{};
+  e.kind = FACT_EPI_BIAS_RESID_F32;
+  e.out_f32 = x;
+  e.ldo = d;
+  e.bias = L.bo;
+  e.resid = x;
+  e.ldr = d;
+  if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, d, L.wo_hi, L.wo_lo, L.wo_f32, M, d, d, &e, st))) return rc;
+  // --- Residual(Norm(MLP))
+  if ((rc = fact_layernorm_split(x, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
+  e = fact_gemm_epilogue{};
+  e.kind = FACT_EPI_BIAS_GELU_SPLIT;
+  e.out_hi = ws.h_hi;
+  e.out_lo = lo ? ws.h_lo : nullptr;
+  e.ldo = ff;
+  e.bias = L.b1;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.w1_hi, L.w1_lo, L.w1_f32, M, ff, d, &e, st))) return rc;
+  e = fact_gemm_epilogue{};
+  e.kind = FACT_EPI_BIAS_RESID_F32;
+  e.out_f32 = dst ? dst : x;
+  e.ldo = d;
+  e.bias = L.b2;
+  e.resid = x;
+  e.ldr = d;
+  if (dst) {
+    e.seq_in = seq;
+    e.seq_out = dst_seq;
+    e.seq_off = dst_off;
+  }
+  return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, M, d, ff, &e, st);
+}
+
+static int run_stack(const fact_dims* dm, const fact_layer_weights* layers, int n_layers, float* x, int batch,
+                     int seq, int mode, const Workspace& ws, float* dst, int dst_seq, int dst_off, cudaStream_t st) {
+  for (int i = 0; i < n_layers; ++i) {
+    const bool last = i + 1 == n_layers;
+    int rc = run_layer(dm, layers[i], x, batch, seq, mode, ws, last ? dst : nullptr, dst_seq, dst_off, st);
+    if (rc) return rc;
+  }
+  return FACT_OK;
+}
+
+// embeddings + modality encoders + 12-layer cross-modal stack; leaves the result in ws.xc
+static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* motion, long long motion_bs,
+                     const float* audio, long long audio_bs, const int* step_ptr, int batch, int mode,
+                     const Workspace& ws, cudaStream_t st) {
+  const int d = dm->d_model, ns = dm->motion_seq + dm->audio_seq;
+  int rc;
+  FACT_REQUIRE(dm->motion_layers > 0 && dm->audio_layers > 0 && dm->cross_layers > 0, FACT_ERR_UNSUPPORTED,
+               "every stack needs at least one layer");
+  if ((rc = fact_embed(motion, motion_bs, step_ptr, w->motion_embed_w, w->motion_embed_b, w->motion_pos, ws.xm, batch,
+                       dm->motion_seq, dm->motion_dim, d, st)))
+    return rc;
+  if ((rc = run_stack(dm, w->motion_layers, dm->motion_layers, ws.xm, batch, dm->motion_seq, mode, ws, ws.xc, ns, 0,
+                      st)))
+    return rc;
+  if ((rc = fact_embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
+                       dm->audio_seq, dm->audio_dim, d, st)))
+    return rc;
+  if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, ws, ws.xc, ns,
+                      dm->motion_seq, st)))
+    return rc;
+  return run_stack(dm, w->cross_layers, dm->cross_layers, ws.xc, batch, ns, mode, ws, nullptr, 0, 0, st);
+}
+
+static int check_weights(const fact_dims* dm, const fact_weights* w) {
+  FACT_REQUIRE(w && w->motion_layers && w->audio_layers && w->cross_layers, FACT_ERR_BAD_SHAPE, "null weights");
+  FACT_REQUIRE(w->motion_embed_w && w->motion_embed_b && w->motion_pos && w->audio_embed_w && w->audio_embed_b &&
+                   w->audio_pos && w->out_w && w->out_b,
+               FACT_ERR_BAD_SHAPE, "null embedding / head weight");
+  (void)dm;
+  return FACT_OK;
+}
+
+// ---- graph cache for the AR loop
+struct GraphKey {
+  std::vector<uintptr_t> v;
+  bool operator<(const GraphKey& o) const { return v < o.v; }
+};
+static std::mutex g_graph_mu;
+static std::map<GraphKey, cudaGraphExec_t> g_graphs;
+
+}  // namespace fact
+
+using namespace fact;
+
+extern "C" size_t fact_workspace_bytes(const fact_dims* dims, int batch, int mode) {
+  if (!dims || batch <= 0) return 0;
+  return carve(dims, batch, mode, nullptr, nullptr);
+}
+
+extern "C" int fact_forward(const fact_dims* dims, const fact_weights* w, const float* motion, const float* audio,
+                            float* out, int batch, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_weights(dims, w))) return rc;
+  FACT_REQUIRE(motion && audio && out && batch > 0, FACT_ERR_BAD_SHAPE, "fact_forward: bad arguments");
+  FACT_REQUIRE(mode >= 0 && mode <= 2, FACT_ERR_UNSUPPORTED, "unknown mode %d", mode);
+  FACT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, FACT_ERR_BAD_ALIGN,
+               "workspace must be 1024-B aligned");
+  Workspace ws;
+  const size_t need = carve(dims, batch, mode, workspace, &ws);
+  FACT_REQUIRE(workspace && workspace_bytes >= need, FACT_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+               workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  const long long mbs = static_cast<long long>(dims->motion_seq) * dims->motion_dim;
+  const long long abs_ = static_cast<long long>(dims->audio_seq) * dims->audio_dim;
+  if ((rc = run_trunk(dims, w, motion, mbs, audio, abs_, nullptr, batch, mode, ws, st))) return rc;
+  // output Dense on all 360 rows (base_models.py:200)
+  const int d = dims->d_model, ns = dims->motion_seq + dims->audio_seq, M = batch * ns;
+  const bool lo = mode != FACT_MODE_BF16;
+  if ((rc = fact_layernorm_split(ws.xc, nullptr, nullptr, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
+  fact_gemm_epilogue e{};
+  e.kind = FACT_EPI_BIAS_F32;
+  e.out_f32 = out;
+  e.ldo = dims->out_dim;
+  e.bias = w->out_b;
+  if (mode == FACT_MODE_FP32_SIMT)
+    return gemm_simt_split(ws.ln_hi, ws.ln_lo, d, w->out_w, M, dims->out_dim, d, &e, st);
+  FACT_REQUIRE(w->out_w_hi && (mode == FACT_MODE_BF16 || w->out_w_lo), FACT_ERR_BAD_SHAPE, "packed head weight missing");
+  return fact_gemm(ws.ln_hi, lo ? ws.ln_lo : nullptr, d, w->out_w_hi, lo ? w->out_w_lo : nullptr, d, M,
+                   dims->out_dim, d, &e, st);
+}
+
+extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist,
+                                          const float* audio, int audio_len, int batch, int n_frames,
+                                          int* step_counter, void* workspace, size_t workspace_bytes, int mode,
+                                          int use_graph, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_weights(dims, w))) return rc;
+  FACT_REQUIRE(motion_hist && audio && step_counter && batch > 0 && n_frames > 0, FACT_ERR_BAD_SHAPE,
+               "fact_infer_auto_regressive: bad arguments");
+  FACT_REQUIRE(audio_len - dims->audio_seq + 1 >= n_frames, FACT_ERR_BAD_SHAPE,
+               "audio_len %d supports only %d frames, %d requested (fact_model.py:125-126 early stop is the caller's)",
+               audio_len, audio_len - dims->audio_seq + 1, n_frames);
+  FACT_REQUIRE(mode >= 0 && mode <= 2, FACT_ERR_UNSUPPORTED, "unknown mode %d", mode);
+  FACT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, FACT_ERR_BAD_ALIGN,
+               "workspace must be 1024-B aligned");
+  Workspace ws;
+  const size_t need = carve(dims, batch, mode, workspace, &ws);
+  FACT_REQUIRE(workspace && workspace_bytes >= need, FACT_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+               workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  const int ns = dims->motion_seq + dims->audio_seq;
+  const long long hist_bs = static_cast<long long>(dims->motion_seq + n_frames) * dims->motion_dim;
+  const long long audio_bs = static_cast<long long>(audio_len) * dims->audio_dim;
+  FACT_REQUIRE(dims->out_dim == dims->motion_dim, FACT_ERR_BAD_SHAPE,
+               "AR feedback needs out_dim == motion feature dim (fact_model.py:131)");
+
+  auto one_frame = [&](cudaStream_t s) -> int {
+    int r;
+    if ((r = run_trunk(dims, w, motion_hist, hist_bs, audio, audio_bs, step_counter, batch, mode, ws, s))) return r;
+    // keep row 0 of each sample (fact_model.py:128), append it to the history at row motion_seq + step
+    if ((r = fact_head_rows(ws.xc, ns, w->out_w, w->out_b,
+                            motion_hist + static_cast<size_t>(dims->motion_seq) * dims->motion_dim, hist_bs,
+                            step_counter, batch, dims->d_model, dims->out_dim, s)))
+      return r;
+    return step_inc(step_counter, s);
+  };
+
+  if ((rc = step_set(step_counter, 0, st))) return rc;
+  if (!use_graph) {
+    for (int i = 0; i < n_frames; ++i)
+      if ((rc = one_frame(st))) return rc;
+    return FACT_OK;
+  }
+  FACT_REQUIRE(st != nullptr, FACT_ERR_UNSUPPORTED,
+               "graph replay needs a non-default stream (capture is illegal on the legacy stream)");
+  GraphKey key;
+  key.v = {reinterpret_cast<uintptr_t>(w->cross_layers[0].wqkv_hi), reinterpret_cast<uintptr_t>(w->out_w),
+           reinterpret_cast<uintptr_t>(motion_hist), reinterpret_cast<uintptr_t>(audio),
+           reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
+           static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(n_frames),
+           static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers),
+           static_cast<uintptr_t>(dims->d_model)};
+  cudaGraphExec_t exec = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    auto it = g_graphs.find(key);
+    if (it != g_graphs.end()) exec = it->second;
+  }
+  if (!exec) {
+    cudaGraph_t graph = nullptr;
+    FACT_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = one_frame(st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    if (g_graphs.size() >= 16) {  // bounded: drop everything (idle graphs only; callers sync between shapes)
+      for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second);
+      g_graphs.clear();
+    }
+    g_graphs[key] = exec;
+  }
+  for (int i = 0; i < n_frames; ++i) FACT_CUDA_CHECK(cudaGraphLaunch(exec, st));
+  return FACT_OK;
+}

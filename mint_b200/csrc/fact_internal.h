@@ -1,0 +1,36 @@
+// Internal (non-ABI) declarations shared by the translation units of libfact_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/fact_sm100.h"
+
+namespace fact {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define FACT_CUDA_CHECK(expr)                                   \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return ::fact::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define FACT_LAUNCH_CHECK(what)                                 \
+  do {                                                          \
+    cudaError_t _e = cudaGetLastError();                        \
+    if (_e != cudaSuccess) return ::fact::cuda_fail(_e, what);  \
+  } while (0)
+
+#define FACT_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      ::fact::set_error(__VA_ARGS__); \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace fact

@@ -1,0 +1,230 @@
+"""FACTModel -- B200-native drop-in for mint/core/fact_model.py:26-148.
+
+Same constructor and methods as the reference class (`FACTModel(config, is_training)`, `__call__(inputs)`,
+`infer_auto_regressive(inputs, steps=1200)`, `loss(target, pred)`, `get_metrics(eval_config)`,
+`trainable_variables`, `losses`, settable `global_step`), but tensors are torch CUDA tensors and all math runs in
+libfact_sm100.so (hand-written sm_100a kernels) through the C ABI of include/fact_sm100.h.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+
+import torch
+
+from . import config_util, lib, weights as W
+
+_TORCH_BF16 = torch.bfloat16
+
+
+class FACTModel:
+    """Audio Motion Multi-Modal model (reference docstring: fact_model.py:26-27)."""
+
+    def __init__(self, config, is_training: bool, device: str | torch.device = "cuda", mode: str = "precise",
+                 seed: int = 0, use_graph: bool = True):
+        """config: mint.protos.FACTModel message (model.proto:27-31); is_training kept for signature parity
+        (the reference only uses it to gate dropout, which FACT never applies)."""
+        self._lib = lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("FACTModel needs a CUDA device (sm_100a); there is no CPU path")
+        self.config = copy.deepcopy(config)
+        self.is_training = is_training
+        self.dims = config_util.resolve_fact_dims(self.config)
+        d = self.dims
+        for enc in (d.motion, d.audio):
+            if (enc.hidden, enc.heads, enc.ff) != (d.cross_hidden, d.cross_heads, d.cross_ff):
+                # the reference raises on a width mismatch at call time (base_models.py:184-189); heads/ff could
+                # differ there, but the C ABI carries one (d, heads, ff) triple
+                raise ValueError("The modal_a hidden size (%d) should be the same with the modal_b hidden size (%d)"
+                                 % (d.motion.hidden, d.audio.hidden))
+        self.device = torch.device(device)
+        if mode not in lib.MODES:
+            raise ValueError(f"mode must be one of {sorted(lib.MODES)}")
+        self.mode = mode
+        self.use_graph = use_graph
+        self.global_step = None        # set by trainer / evaluator (trainer.py:151, evaluator.py:57)
+        self.losses = []               # Keras regularisation losses: none in FACT
+        self._params: dict[str, torch.Tensor] = {}
+        self._packed: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}
+        self._ws: dict[tuple, torch.Tensor] = {}
+        self._side_stream = None
+        self._step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._cdims = lib.Dims(d.cross_hidden, d.cross_heads, d.cross_ff, d.motion.layers, d.audio.layers,
+                               d.cross_layers, d.motion.seq_len, d.audio.seq_len, d.motion.feature_dim,
+                               d.audio.feature_dim, d.out_dim)
+        self.set_weights(W.keras_default_init(d, seed))
+
+    # ------------------------------------------------------------------ variables
+    @property
+    def trainable_variables(self):
+        return list(self._params.values())
+
+    def variable_names(self):
+        return list(self._params.keys())
+
+    def get_weights(self) -> dict:
+        return {k: v.detach().clone() for k, v in self._params.items()}
+
+    def set_weights(self, weights: dict) -> None:
+        """weights: name -> array-like in Keras layout (see mint_b200/weights.py for the names)."""
+        shapes = W.variable_shapes(self.dims)
+        missing = set(shapes) - set(weights)
+        extra = set(weights) - set(shapes)
+        if missing or extra:
+            raise KeyError(f"weight names mismatch: missing {sorted(missing)[:3]} extra {sorted(extra)[:3]}")
+        for name, shp in shapes.items():
+            t = torch.as_tensor(weights[name]).to(torch.float32)
+            if tuple(t.shape) != tuple(shp):
+                raise ValueError(f"{name}: shape {tuple(t.shape)} != {shp}")
+            t = t.to(self.device).contiguous()
+            if name in self._params:
+                self._params[name].copy_(t)
+            else:
+                self._params[name] = t.clone()
+        self.repack()
+
+    def repack(self) -> None:
+        """(Re)build the K-major bf16 hi/lo copies the tensor-core GEMMs read (after any weight update)."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            for name, p in self._params.items():
+                if not name.endswith("/kernel") or "linear_embedding" in name:
+                    continue
+                k_in, n_out = p.shape
+                if name not in self._packed:
+                    self._packed[name] = (torch.empty((n_out, k_in), dtype=_TORCH_BF16, device=self.device),
+                                          torch.empty((n_out, k_in), dtype=_TORCH_BF16, device=self.device))
+                hi, lo = self._packed[name]
+                lib.check(self._lib.fact_pack_weight(p.data_ptr(), hi.data_ptr(), lo.data_ptr(), k_in, n_out, st),
+                          "fact_pack_weight")
+        self._build_tables()
+
+    def _build_tables(self) -> None:
+        P, K = self._params, self._packed
+        precise = self.mode != "bf16"
+
+        def layer(prefix: str) -> lib.LayerWeights:
+            g = lambda s: P[f"{prefix}/{s}"].data_ptr()
+            hi = lambda s: K[f"{prefix}/{s}"][0].data_ptr()
+            lo = lambda s: K[f"{prefix}/{s}"][1].data_ptr() if precise else None
+            return lib.LayerWeights(
+                g("attn/norm/gamma"), g("attn/norm/beta"), hi("attn/to_qkv/kernel"), lo("attn/to_qkv/kernel"),
+                hi("attn/to_out/kernel"), lo("attn/to_out/kernel"), g("attn/to_out/bias"),
+                g("mlp/norm/gamma"), g("mlp/norm/beta"), hi("mlp/dense_0/kernel"), lo("mlp/dense_0/kernel"),
+                g("mlp/dense_0/bias"), hi("mlp/dense_1/kernel"), lo("mlp/dense_1/kernel"), g("mlp/dense_1/bias"),
+                g("attn/to_qkv/kernel"), g("attn/to_out/kernel"), g("mlp/dense_0/kernel"), g("mlp/dense_1/kernel"))
+
+        d = self.dims
+        self._lw_motion = (lib.LayerWeights * d.motion.layers)(
+            *[layer(f"motion_transformer/layer_{i}") for i in range(d.motion.layers)])
+        self._lw_audio = (lib.LayerWeights * d.audio.layers)(
+            *[layer(f"audio_transformer/layer_{i}") for i in range(d.audio.layers)])
+        self._lw_cross = (lib.LayerWeights * d.cross_layers)(
+            *[layer(f"cross_modal_layer/transformer/layer_{i}") for i in range(d.cross_layers)])
+        ok, ob = "cross_modal_layer/output/kernel", "cross_modal_layer/output/bias"
+        self._cw = lib.Weights(
+            self._lw_motion, self._lw_audio, self._lw_cross,
+            P["motion_linear_embedding/kernel"].data_ptr(), P["motion_linear_embedding/bias"].data_ptr(),
+            P["motion_pos_embedding"].data_ptr(),
+            P["audio_linear_embedding/kernel"].data_ptr(), P["audio_linear_embedding/bias"].data_ptr(),
+            P["audio_pos_embedding"].data_ptr(),
+            P[ok].data_ptr(), P[ob].data_ptr(), K[ok][0].data_ptr(), K[ok][1].data_ptr() if precise else None)
+
+    # ------------------------------------------------------------------ plumbing
+    def _workspace(self, batch: int):
+        mode = lib.MODES[self.mode]
+        key = (batch, mode)
+        if key not in self._ws:
+            need = self._lib.fact_workspace_bytes(C.byref(self._cdims), batch, mode)
+            self._ws.clear()  # one live workspace: shapes change rarely and the buffers are large
+            self._ws[key] = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        buf = self._ws[key]
+        base = (buf.data_ptr() + 1023) & ~1023
+        return base, buf.numel() - (base - buf.data_ptr())
+
+    def _to_dev(self, t, last_dim: int, what: str) -> torch.Tensor:
+        t = torch.as_tensor(t)
+        if t.dim() != 3 or t.shape[-1] != last_dim:
+            raise ValueError(f"{what} must be [batch, seq, {last_dim}], got {tuple(t.shape)}")
+        return t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    # ------------------------------------------------------------------ the reference interface
+    def __call__(self, inputs: dict, training: bool = False) -> torch.Tensor:
+        """Single forward pass (fact_model.py:72-101).  inputs["motion_input"]: [B, 120, 225],
+        inputs["audio_input"]: [B, 240, 35]; other keys are ignored.  Returns [B, 360, 225]."""
+        d = self.dims
+        motion = self._to_dev(inputs["motion_input"], d.motion.feature_dim, "motion_input")
+        audio = self._to_dev(inputs["audio_input"], d.audio.feature_dim, "audio_input")
+        if motion.shape[1] != d.motion.seq_len or audio.shape[1] != d.audio.seq_len:
+            # PositionEmbedding adds a [seq, dim] table (base_models.py:154-156): other lengths fail to broadcast
+            raise ValueError(f"sequence lengths must be {d.motion.seq_len}/{d.audio.seq_len}, got "
+                             f"{motion.shape[1]}/{audio.shape[1]}")
+        if motion.shape[0] != audio.shape[0]:
+            raise ValueError("motion_input and audio_input batch sizes differ")
+        batch = motion.shape[0]
+        out = torch.empty((batch, d.cross_seq, d.out_dim), dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self._workspace(batch)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            lib.check(self._lib.fact_forward(C.byref(self._cdims), C.byref(self._cw), motion.data_ptr(),
+                                             audio.data_ptr(), out.data_ptr(), batch, ws, ws_bytes,
+                                             lib.MODES[self.mode], st), "fact_forward")
+        return out
+
+    call = __call__
+
+    def infer_auto_regressive(self, inputs: dict, steps: int = 1200) -> torch.Tensor:
+        """Auto-regressive generation (fact_model.py:103-132): returns [B, n, 225], n = min(steps, T_audio - 239)."""
+        d = self.dims
+        motion = self._to_dev(inputs["motion_input"], d.motion.feature_dim, "motion_input")
+        audio = self._to_dev(inputs["audio_input"], d.audio.feature_dim, "audio_input")
+        if motion.shape[1] != d.motion.seq_len:
+            raise ValueError(f"motion seed must have {d.motion.seq_len} frames")
+        if motion.shape[0] != audio.shape[0]:
+            raise ValueError("motion_input and audio_input batch sizes differ")
+        batch, audio_len = audio.shape[0], audio.shape[1]
+        n = min(int(steps), audio_len - d.audio.seq_len + 1)   # the loop breaks on the first short window (:125-126)
+        if n <= 0:
+            raise ValueError("no full audio window: tf.concat of an empty list fails in the reference too")
+        hist = torch.empty((batch, d.motion.seq_len + n, d.motion.feature_dim), dtype=torch.float32,
+                           device=self.device)
+        hist[:, :d.motion.seq_len].copy_(motion)
+        ws, ws_bytes = self._workspace(batch)
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            run = cur
+            if self.use_graph and cur.cuda_stream == 0:       # stream capture is illegal on the legacy stream
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(self.device)
+                run = self._side_stream
+                run.wait_stream(cur)
+            lib.check(self._lib.fact_infer_auto_regressive(
+                C.byref(self._cdims), C.byref(self._cw), hist.data_ptr(), audio.data_ptr(), audio_len, batch, n,
+                self._step_counter.data_ptr(), ws, ws_bytes, lib.MODES[self.mode], 1 if self.use_graph else 0,
+                run.cuda_stream), "fact_infer_auto_regressive")
+            if run is not cur:
+                cur.wait_stream(run)
+                for t in (hist, audio, motion):
+                    t.record_stream(run)
+        return hist[:, d.motion.seq_len:].contiguous()
+
+    def loss(self, target, pred) -> torch.Tensor:
+        """L2 motion generation loss on the first target_seq_len frames (fact_model.py:134-148)."""
+        pred = torch.as_tensor(pred).to(self.device, torch.float32).contiguous()
+        target = torch.as_tensor(target).to(self.device, torch.float32).contiguous()
+        b, n, od = pred.shape
+        t_len = target.shape[1]
+        out = torch.empty((), dtype=torch.float32, device=self.device)
+        partial = torch.empty(1024, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            lib.check(self._lib.fact_mse(target.data_ptr(), pred.data_ptr(), out.data_ptr(), None,
+                                         partial.data_ptr(), b, t_len, n, od, 1.0, st), "fact_mse")
+        return out
+
+    def compute_motion_generation_loss(self, pred_tensors, target_tensors):
+        return self.loss(target_tensors, pred_tensors)
+
+    def get_metrics(self, eval_config):
+        """Metrics are computed offline in the reference (fact_model.py:138-141)."""
+        return []

@@ -1,0 +1,253 @@
+"""Per-kernel parity tests on the GPU, each through the C ABI, against plain torch fp32/fp64 math."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+from mint_b200 import lib as L
+from tests.helpers import join, rel_err, split_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _epi(**kw):
+    e = L.GemmEpilogue()
+    for k, v in kw.items():
+        setattr(e, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    return e
+
+
+@pytest.mark.parametrize("rows,d", [(7, 800), (257, 800), (33, 64), (5, 1024)])
+@pytest.mark.parametrize("norm", [True, False])
+def test_layernorm_split(fact_lib, cuda, rows, d, norm):
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = (torch.randn(rows, d, generator=g) * 3 + 0.5).to(cuda)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(d, generator=g)).to(cuda)
+    hi = torch.empty(rows, d, dtype=torch.bfloat16, device=cuda)
+    lo = torch.empty_like(hi)
+    L.check(fact_lib.fact_layernorm_split(x.data_ptr(), gamma.data_ptr() if norm else None,
+                                          beta.data_ptr() if norm else None, hi.data_ptr(), lo.data_ptr(), rows, d,
+                                          _st()))
+    ref = torch.nn.functional.layer_norm(x.double(), (d,), gamma.double(), beta.double(), 1e-5) if norm else x.double()
+    got = join(hi, lo).double()
+    assert (got - ref).abs().max() < 2e-5 * max(1.0, float(ref.abs().max()))
+    # hi alone is the bf16 rounding of the value
+    assert (hi.float().double() - ref).abs().max() < 2 ** -8 * float(ref.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("k,n", [(800, 2400), (3072, 800), (35, 800), (800, 225)])
+def test_pack_weight(fact_lib, cuda, k, n):
+    w = torch.randn(k, n, device=cuda) * 0.05
+    hi = torch.empty(n, k, dtype=torch.bfloat16, device=cuda)
+    lo = torch.empty_like(hi)
+    L.check(fact_lib.fact_pack_weight(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), k, n, _st()))
+    rh, rl = split_ref(w.t().contiguous())
+    assert torch.equal(hi, rh) and torch.equal(lo, rl)
+
+
+def _gemm_case(fact_lib, cuda, m, n, k, kind, precise, seed=0, remap=None):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    w = (torch.randn(k, n, generator=g) * (1.0 / math.sqrt(k))).to(cuda)     # Keras layout
+    bias = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    resid = torch.randn(m, n, generator=g).to(cuda)
+    a_hi, a_lo = split_ref(a)
+    w_hi, w_lo = split_ref(w.t().contiguous())
+    if precise:
+        a_eff, w_eff = join(a_hi, a_lo).double(), join(w_hi, w_lo).double()
+    else:
+        a_eff, w_eff = a_hi.double(), w_hi.double()
+    acc = a_eff @ w_eff.t()
+    scale, scale_cols = 0.37, n // 3
+    e = L.GemmEpilogue()
+    e.kind = kind
+    out_rows = m
+    if kind in (L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT):
+        o_hi = torch.zeros(m, n, dtype=torch.bfloat16, device=cuda)
+        o_lo = torch.zeros_like(o_hi)
+        e.out_hi, e.out_lo, e.ldo = o_hi.data_ptr(), o_lo.data_ptr(), n
+        e.bias = bias.data_ptr()
+        e.scale, e.scale_cols = scale, scale_cols
+    else:
+        if remap:
+            seq_in, seq_out, seq_off = remap
+            out_rows = (m // seq_in) * seq_out
+            e.seq_in, e.seq_out, e.seq_off = seq_in, seq_out, seq_off
+        out = torch.full((out_rows, n), float("nan"), device=cuda)
+        e.out_f32, e.ldo = out.data_ptr(), n
+        e.bias = bias.data_ptr()
+        e.resid, e.ldr = resid.data_ptr(), n
+    L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, k, w_hi.data_ptr(),
+                               w_lo.data_ptr() if precise else None, k, m, n, k, C.byref(e), _st()), "fact_gemm")
+    torch.cuda.synchronize()
+    if kind == L.EPI_SPLIT:
+        ref = acc.clone()
+        ref[:, :scale_cols] *= scale
+        got = join(o_hi, o_lo).double()
+    elif kind == L.EPI_BIAS_GELU_SPLIT:
+        ref = torch.nn.functional.gelu(acc + bias.double(), approximate="tanh")
+        got = join(o_hi, o_lo).double()
+    elif kind == L.EPI_BIAS_RESID_F32:
+        ref = acc + bias.double() + resid.double()
+        got = out.double()
+        if remap:
+            idx = torch.arange(m, device=cuda)
+            rows = (idx // seq_in) * seq_out + seq_off + idx % seq_in
+            untouched = torch.ones(out_rows, dtype=torch.bool, device=cuda)
+            untouched[rows] = False
+            assert torch.isnan(out[untouched]).all(), "remapped epilogue wrote outside its rows"
+            got = got[rows]
+    else:
+        ref = acc + bias.double()
+        got = out.double()
+    # vs the exact product of the operands the kernel was given: only fp32 accumulation + output rounding remain
+    tol = 3e-5 if precise else 2e-5
+    assert rel_err(got, ref) < tol, (rel_err(got, ref), m, n, k, kind, precise)
+    if precise:  # and the split operands reproduce the fp32 GEMM
+        full = a.double() @ w.double()
+        if kind == L.EPI_BIAS_F32:
+            assert rel_err(got, full + bias.double()) < 1e-4
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32])
+@pytest.mark.parametrize("m,n,k", [(128, 160, 64), (360, 2400, 800), (300, 800, 3072), (250, 3072, 800),
+                                   (240, 226, 800), (77, 128, 72)])
+def test_gemm_tc(fact_lib, cuda, m, n, k, kind, precise):
+    _gemm_case(fact_lib, cuda, m, n, k, kind, precise)
+
+
+def test_gemm_tc_remap(fact_lib, cuda):
+    _gemm_case(fact_lib, cuda, 3 * 120, 800, 3072, L.EPI_BIAS_RESID_F32, True, remap=(120, 360, 0))
+    _gemm_case(fact_lib, cuda, 3 * 240, 800, 3072, L.EPI_BIAS_RESID_F32, False, remap=(240, 360, 120))
+
+
+def test_gemm_tc_inplace_residual(fact_lib, cuda):
+    """out-proj / FF2 write the residual stream in place (out == resid)."""
+    m, n, k = 360, 800, 800
+    a = torch.randn(m, k, device=cuda)
+    w = torch.randn(k, n, device=cuda) / math.sqrt(k)
+    x = torch.randn(m, n, device=cuda)
+    x0 = x.clone()
+    bias = torch.randn(n, device=cuda)
+    a_hi, a_lo = split_ref(a)
+    w_hi, w_lo = split_ref(w.t().contiguous())
+    e = _epi(kind=L.EPI_BIAS_RESID_F32, out_f32=x, ldo=n, bias=bias, resid=x, ldr=n)
+    L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr(), k, w_hi.data_ptr(), w_lo.data_ptr(), k, m, n, k,
+                               C.byref(e), _st()))
+    ref = join(a_hi, a_lo).double() @ join(w_hi, w_lo).double().t() + bias.double() + x0.double()
+    assert rel_err(x, ref) < 3e-5
+
+
+def test_gemm_big_tiles(fact_lib, cuda):
+    """Many CTAs / several waves, K pipeline wraps many times."""
+    _gemm_case(fact_lib, cuda, 4096 + 40, 3072, 800, L.EPI_BIAS_GELU_SPLIT, True, seed=3)
+    _gemm_case(fact_lib, cuda, 2048, 800, 3072, L.EPI_BIAS_RESID_F32, False, seed=4)
+
+
+@pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32])
+def test_gemm_f32(fact_lib, cuda, kind):
+    m, n, k = 130, 200, 225
+    a = torch.randn(m, k, device=cuda)
+    w = torch.randn(k, n, device=cuda) / math.sqrt(k)
+    bias = torch.randn(n, device=cuda)
+    resid = torch.randn(m, n, device=cuda)
+    o_hi = torch.zeros(m, n, dtype=torch.bfloat16, device=cuda)
+    o_lo = torch.zeros_like(o_hi)
+    out = torch.zeros(m, n, device=cuda)
+    e = _epi(kind=kind, out_f32=out, out_hi=o_hi, out_lo=o_lo, ldo=n, bias=bias, resid=resid, ldr=n, scale=0.5,
+             scale_cols=100)
+    L.check(fact_lib.fact_gemm_f32(a.data_ptr(), k, w.data_ptr(), m, n, k, C.byref(e), _st()))
+    acc = a.double() @ w.double()
+    if kind == L.EPI_SPLIT:
+        ref = acc.clone(); ref[:, :100] *= 0.5; got = join(o_hi, o_lo)
+    elif kind == L.EPI_BIAS_GELU_SPLIT:
+        ref = torch.nn.functional.gelu(acc + bias.double(), approximate="tanh"); got = join(o_hi, o_lo)
+    elif kind == L.EPI_BIAS_RESID_F32:
+        ref = acc + bias.double() + resid.double(); got = out
+    else:
+        ref = acc + bias.double(); got = out
+    assert rel_err(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("batch,n,heads,dh", [(2, 120, 10, 80), (1, 240, 10, 80), (2, 360, 10, 80), (3, 37, 2, 16),
+                                              (1, 128, 3, 64), (1, 65, 4, 32)])
+def test_sdpa(fact_lib, cuda, batch, n, heads, dh, precise):
+    d = heads * dh
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv = torch.randn(batch * n, 3 * d, generator=g).to(cuda)
+    qkv[:, :d] *= 1.5   # stands for q * scale * log2(e)
+    hi, lo = split_ref(qkv)
+    o_hi = torch.zeros(batch * n, d, dtype=torch.bfloat16, device=cuda)
+    o_lo = torch.zeros_like(o_hi)
+    L.check(fact_lib.fact_sdpa(hi.data_ptr(), lo.data_ptr() if precise else None, o_hi.data_ptr(),
+                               o_lo.data_ptr() if precise else None, batch, n, heads, dh, _st()))
+    eff = (join(hi, lo) if precise else hi.float()).double().view(batch, n, 3, heads, dh)
+    q, k, v = (eff[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s = q @ k.transpose(-1, -2)                       # log2 domain
+    p = torch.softmax(s * math.log(2.0), dim=-1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(batch * n, d)
+    got = join(o_hi, o_lo if precise else None).double()
+    tol = 5e-5 if precise else 2e-2   # bf16 mode rounds p and the output to 8 bits
+    assert (got - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), float((got - ref).abs().max())
+
+
+def test_embed_and_offsets(fact_lib, cuda):
+    batch, x_len, n_tok, f, d = 3, 50, 12, 35, 64
+    x = torch.randn(batch, x_len, f, device=cuda)
+    w = torch.randn(f, d, device=cuda)
+    b = torch.randn(d, device=cuda)
+    pos = torch.randn(n_tok, d, device=cuda)
+    y = torch.empty(batch * n_tok, d, device=cuda)
+    step = torch.tensor([7], dtype=torch.int32, device=cuda)
+    for sp, start in ((None, 0), (step, 7)):
+        L.check(fact_lib.fact_embed(x.data_ptr(), x_len * f, sp.data_ptr() if sp is not None else None, w.data_ptr(),
+                                    b.data_ptr(), pos.data_ptr(), y.data_ptr(), batch, n_tok, f, d, _st()))
+        ref = x[:, start:start + n_tok].double() @ w.double() + b.double() + pos.double()
+        assert rel_err(y.view(batch, n_tok, d), ref) < 1e-5
+
+
+def test_head_rows(fact_lib, cuda):
+    batch, seq, d, od, frames = 4, 9, 800, 225, 5
+    x = torch.randn(batch * seq, d, device=cuda)
+    w = torch.randn(d, od, device=cuda) * 0.02
+    b = torch.randn(od, device=cuda)
+    out = torch.zeros(batch, frames, od, device=cuda)
+    step = torch.tensor([3], dtype=torch.int32, device=cuda)
+    L.check(fact_lib.fact_head_rows(x.data_ptr(), seq, w.data_ptr(), b.data_ptr(), out.data_ptr(), frames * od,
+                                    step.data_ptr(), batch, d, od, _st()))
+    ref = x.view(batch, seq, d)[:, 0].double() @ w.double() + b.double()
+    assert rel_err(out[:, 3], ref) < 1e-5
+    assert float(out[:, :3].abs().max()) == 0 and float(out[:, 4:].abs().max()) == 0
+
+
+def test_mse(fact_lib, cuda):
+    b, n, t, od = 5, 36, 20, 225
+    pred = torch.randn(b, n, od, device=cuda)
+    target = torch.randn(b, t, od, device=cuda)
+    loss = torch.zeros((), device=cuda)
+    dpred = torch.full((b, n, od), 7.0, device=cuda)
+    partial = torch.zeros(1024, device=cuda)
+    L.check(fact_lib.fact_mse(target.data_ptr(), pred.data_ptr(), loss.data_ptr(), dpred.data_ptr(),
+                              partial.data_ptr(), b, t, n, od, 0.25, _st()))
+    p = pred.double().requires_grad_(True)
+    ref = ((target.double() - p[:, :t]) ** 2).mean()
+    (ref * 0.25).backward()
+    assert abs(float(loss) - float(ref)) < 1e-6 * float(ref)
+    assert rel_err(dpred, p.grad) < 1e-5
+
+
+def test_errors_are_reported(fact_lib, cuda):
+    e = L.GemmEpilogue()
+    rc = fact_lib.fact_gemm(None, None, 8, None, None, 8, 1, 1, 8, C.byref(e), None)
+    assert rc == -1 and b"null" in fact_lib.fact_last_error()
+    x = torch.zeros(4, 6, device=cuda)
+    rc = fact_lib.fact_layernorm_split(x.data_ptr(), None, None, x.data_ptr(), None, 4, 6, None)
+    assert rc == -1
