@@ -178,15 +178,17 @@ FACT_API size_t fact_workspace_bytes(const fact_dims* dims, int batch, int mode)
 FACT_API int fact_forward(const fact_dims* dims, const fact_weights* w, const float* motion, const float* audio, float* out,
                  int batch, void* workspace, size_t workspace_bytes, int mode, void* stream);
 
-/* FACTModel.infer_auto_regressive (fact_model.py:103-132).
- * motion_hist: [B, motion_seq + n_frames, motion_dim]; the first motion_seq rows hold the seed, frames are appended
- * in place (the shift-by-one of fact_model.py:131 is an index offset into this buffer).
- * audio: [B, audio_len, audio_dim].  n_frames must be <= min(steps, audio_len - audio_seq + 1) (the caller applies
- * the early-stop rule of fact_model.py:125-126).  step_counter: device int scratch.
- * use_graph != 0 replays one captured CUDA graph per frame. */
-FACT_API int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist, const float* audio,
-                               int audio_len, int batch, int n_frames, int* step_counter, void* workspace,
-                               size_t workspace_bytes, int mode, int use_graph, void* stream);
+/* FACTModel.infer_auto_regressive (fact_model.py:103-132), frames [start_frame, start_frame + n_frames).
+ * motion_hist: [B, motion_seq + hist_capacity, motion_dim]; the first motion_seq rows hold the seed, generated frames
+ * are appended in place (the shift-by-one of fact_model.py:131 is an index offset into this buffer), so a call with
+ * start_frame > 0 continues a previous one.  audio: [B, audio_len, audio_dim].
+ * start_frame + n_frames must be <= min(hist_capacity, audio_len - audio_seq + 1) (the caller applies the early-stop
+ * rule of fact_model.py:125-126).  step_counter: device int scratch.
+ * use_graph != 0 replays one captured CUDA graph per frame (needs a non-default stream). */
+FACT_API int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist,
+                                        int hist_capacity, const float* audio, int audio_len, int batch,
+                                        int start_frame, int n_frames, int* step_counter, void* workspace,
+                                        size_t workspace_bytes, int mode, int use_graph, void* stream);
 
 #ifdef __cplusplus
 }

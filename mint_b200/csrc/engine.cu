@@ -223,17 +223,19 @@ extern "C" int fact_forward(const fact_dims* dims, const fact_weights* w, const 
 }
 
 extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist,
-                                          const float* audio, int audio_len, int batch, int n_frames,
-                                          int* step_counter, void* workspace, size_t workspace_bytes, int mode,
-                                          int use_graph, void* stream) {
+                                          int hist_capacity, const float* audio, int audio_len, int batch,
+                                          int start_frame, int n_frames, int* step_counter, void* workspace,
+                                          size_t workspace_bytes, int mode, int use_graph, void* stream) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_weights(dims, w))) return rc;
-  FACT_REQUIRE(motion_hist && audio && step_counter && batch > 0 && n_frames > 0, FACT_ERR_BAD_SHAPE,
-               "fact_infer_auto_regressive: bad arguments");
-  FACT_REQUIRE(audio_len - dims->audio_seq + 1 >= n_frames, FACT_ERR_BAD_SHAPE,
+  FACT_REQUIRE(motion_hist && audio && step_counter && batch > 0 && n_frames > 0 && start_frame >= 0,
+               FACT_ERR_BAD_SHAPE, "fact_infer_auto_regressive: bad arguments");
+  FACT_REQUIRE(start_frame + n_frames <= hist_capacity, FACT_ERR_BAD_SHAPE,
+               "frames [%d, %d) exceed the history capacity %d", start_frame, start_frame + n_frames, hist_capacity);
+  FACT_REQUIRE(audio_len - dims->audio_seq + 1 >= start_frame + n_frames, FACT_ERR_BAD_SHAPE,
                "audio_len %d supports only %d frames, %d requested (fact_model.py:125-126 early stop is the caller's)",
-               audio_len, audio_len - dims->audio_seq + 1, n_frames);
+               audio_len, audio_len - dims->audio_seq + 1, start_frame + n_frames);
   FACT_REQUIRE(mode >= 0 && mode <= 2, FACT_ERR_UNSUPPORTED, "unknown mode %d", mode);
   FACT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, FACT_ERR_BAD_ALIGN,
                "workspace must be 1024-B aligned");
@@ -243,7 +245,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
                workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
   const int ns = dims->motion_seq + dims->audio_seq;
-  const long long hist_bs = static_cast<long long>(dims->motion_seq + n_frames) * dims->motion_dim;
+  const long long hist_bs = static_cast<long long>(dims->motion_seq + hist_capacity) * dims->motion_dim;
   const long long audio_bs = static_cast<long long>(audio_len) * dims->audio_dim;
   FACT_REQUIRE(dims->out_dim == dims->motion_dim, FACT_ERR_BAD_SHAPE,
                "AR feedback needs out_dim == motion feature dim (fact_model.py:131)");
@@ -259,7 +261,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
     return step_inc(step_counter, s);
   };
 
-  if ((rc = step_set(step_counter, 0, st))) return rc;
+  if ((rc = step_set(step_counter, start_frame, st))) return rc;
   if (!use_graph) {
     for (int i = 0; i < n_frames; ++i)
       if ((rc = one_frame(st))) return rc;
@@ -271,7 +273,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
   key.v = {reinterpret_cast<uintptr_t>(w->cross_layers[0].wqkv_hi), reinterpret_cast<uintptr_t>(w->out_w),
            reinterpret_cast<uintptr_t>(motion_hist), reinterpret_cast<uintptr_t>(audio),
            reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
-           static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(n_frames),
+           static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(hist_capacity),
            static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers),
            static_cast<uintptr_t>(dims->d_model)};
   cudaGraphExec_t exec = nullptr;

@@ -24,7 +24,8 @@ namespace fact {
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // one 128-byte swizzle span of bf16
 constexpr int UMMA_K = 16;    // bf16
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
 struct EpiArgs {
@@ -38,18 +39,22 @@ struct EpiArgs {
   float scale;
   int scale_cols;
   int seq_in, seq_out, seq_off;
+  int vec_ok;  // all row pitches / base pointers allow 16-byte row-chunk accesses
 };
 
 template <int BN, int NPART, int STAGES>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NPART * (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+  static constexpr int ACC_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
+                                   : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
-  static_assert(STAGE_BYTES >= 4 * 32 * 33 * 4, "epilogue scratch aliases stage 0");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=128 / 32-column epilogue chunks");
+  static_assert(ACC_COLS <= 512, "TMEM has 512 columns");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+  static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier block too small");
 };
 
 __device__ __forceinline__ int map_row(int row, const EpiArgs& e) {
@@ -57,26 +62,109 @@ __device__ __forceinline__ int map_row(int row, const EpiArgs& e) {
   return (row / e.seq_in) * e.seq_out + e.seq_off + (row % e.seq_in);
 }
 
+// One 32-column chunk of one accumulator row (this thread's row): fused epilogue + global store.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const float* v, const float4* rv, int row, int col0, bool row_ok,
+                                               bool fast, int N, const EpiArgs& ep) {
+  if (EPI == FACT_EPI_BIAS_RESID_F32 || EPI == FACT_EPI_BIAS_F32) {
+    if (!row_ok) return;
+    float* orow = ep.out_f32 + static_cast<size_t>(map_row(row, ep)) * ep.ldo + col0;
+    if (fast) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = ep.bias ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = v[4 * i + 0] + b.x;
+        o.y = v[4 * i + 1] + b.y;
+        o.z = v[4 * i + 2] + b.z;
+        o.w = v[4 * i + 3] + b.w;
+        if (EPI == FACT_EPI_BIAS_RESID_F32) {
+          o.x += rv[i].x;
+          o.y += rv[i].y;
+          o.z += rv[i].z;
+          o.w += rv[i].w;
+        }
+        reinterpret_cast<float4*>(orow)[i] = o;
+      }
+    } else {
+      const float* rrow = ep.resid + static_cast<size_t>(row) * ep.ldr + col0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (col0 + c < N) {
+          float x = v[c] + (ep.bias ? ep.bias[col0 + c] : 0.f);
+          if (EPI == FACT_EPI_BIAS_RESID_F32) x += rrow[c];
+          orow[c] = x;
+        }
+      }
+    }
+  } else {
+    if (!row_ok) return;
+    const size_t o = static_cast<size_t>(row) * ep.ldo + col0;
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
+        const float b = (fast || col0 + c < N) ? __ldg(ep.bias + col0 + c) : 0.f;
+        x[c] = gelu_tanh(v[c] + b);
+      } else {
+        x[c] = (col0 + c < ep.scale_cols) ? v[c] * ep.scale : v[c];
+      }
+    }
+    if (fast) {
+      uint32_t h[16], l[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(x[2 * c], h0, l0);
+        split_bf16(x[2 * c + 1], h1, l1);
+        h[c] = pack_bf16x2(h0, h1);
+        l[c] = pack_bf16x2(l0, l1);
+      }
+      uint4* ph = reinterpret_cast<uint4*>(ep.out_hi + o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ph[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      if (ep.out_lo) {
+        uint4* pl = reinterpret_cast<uint4*>(ep.out_lo + o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pl[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (col0 + c < N) {
+          bf16 h0, l0;
+          split_bf16(x[c], h0, l0);
+          ep.out_hi[o + c] = h0;
+          if (ep.out_lo) ep.out_lo[o + c] = l0;
+        }
+      }
+    }
+  }
+}
+
+// Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c + grid, ... (n fastest, so co-resident CTAs share A
+// rows in L2).  TMEM holds two BN-column accumulators: the MMA warp fills one while the epilogue warps drain the other.
 template <int BN, int NPART, int STAGES, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
     const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, int M, int N, int K,
-    EpiArgs ep) {
+    int tiles_n, int num_tiles, EpiArgs ep) {
   using Cfg = GemmCfg<BN, NPART, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barrier block: full[STAGES] | empty[STAGES] | tmem_full | tmem_ptr
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 1);
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 1));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -90,7 +178,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_addr);
@@ -106,110 +197,95 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-        tma_load_2d(sA(s, 0), &tmA0, kb * BK, m0, full_bar(s));
-        tma_load_2d(sB(s, 0), &tmB0, kb * BK, n0, full_bar(s));
-        if (NPART == 2) {
-          tma_load_2d(sA(s, 1), &tmA1, kb * BK, m0, full_bar(s));
-          tma_load_2d(sB(s, 1), &tmB1, kb * BK, n0, full_bar(s));
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          tma_load_2d(sA(s, 0), &tmA0, kb * BK, m0, full_bar(s));
+          tma_load_2d(sB(s, 0), &tmB0, kb * BK, n0, full_bar(s));
+          if (NPART == 2) {
+            tma_load_2d(sA(s, 1), &tmA1, kb * BK, m0, full_bar(s));
+            tma_load_2d(sB(s, 1), &tmB1, kb * BK, n0, full_bar(s));
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-          const uint32_t koff = kk * UMMA_K * 2;  // bytes inside the 128-B swizzle span
-          const uint64_t a_hi = umma_desc_k_sw128(sA(s, 0) + koff);
-          const uint64_t b_hi = umma_desc_k_sw128(sB(s, 0) + koff);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-          if (NPART == 2) {
-            const uint64_t a_lo = umma_desc_k_sw128(sA(s, 1) + koff);
-            const uint64_t b_lo = umma_desc_k_sw128(sB(s, 1) + koff);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint32_t koff = kk * UMMA_K * 2;  // bytes inside the 128-B swizzle span
+            const uint64_t a_hi = umma_desc_k_sw128(sA(s, 0) + koff);
+            const uint64_t b_hi = umma_desc_k_sw128(sB(s, 0) + koff);
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            if (NPART == 2) {
+              const uint64_t a_lo = umma_desc_k_sw128(sA(s, 1) + koff);
+              const uint64_t b_lo = umma_desc_k_sw128(sB(s, 1) + koff);
+              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+            }
           }
+          umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
         }
-        umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
+        umma_commit(tmem_full_bar(acc));
       }
-      umma_commit(tmem_full_bar);
     }
-  } else {  // ---------------- epilogue warps 2..5 ; TMEM lane quadrant = warp % 4
-    const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    // all MMAs (hence all TMA loads) are complete: stage 0 is free to serve as the transpose scratch
-    float* scratch = reinterpret_cast<float*>(smem_gen) + q * (32 * 33);
-    const int row_base = m0 + q * 32;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
+  } else {  // ---------------- epilogue warps 2..9 ; TMEM lane quadrant = warp % 4, chunk parity = (warp - 2) / 4
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      // prefetch the first residual chunk while the MMAs of this tile are still running
+      float4 rv[8];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) scratch[lane * 33 + c] = v[c];
-      __syncwarp();
-      if (EPI == FACT_EPI_BIAS_RESID_F32 || EPI == FACT_EPI_BIAS_F32) {
-        const int col = n0 + c0 + lane;
-        const bool cok = col < N;
-        const float b = (cok && ep.bias) ? ep.bias[col] : 0.f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int row = row_base + r;
-          if (row < M && cok) {
-            float x = scratch[r * 33 + lane] + b;
-            if (EPI == FACT_EPI_BIAS_RESID_F32) x += ep.resid[static_cast<size_t>(row) * ep.ldr + col];
-            ep.out_f32[static_cast<size_t>(map_row(row, ep)) * ep.ldo + col] = x;
-          }
-        }
-      } else {
-        const int cp = (lane & 15) * 2;
-        const int col = n0 + c0 + cp;
-        float b0 = 0.f, b1 = 0.f;
-        if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
-          if (col < N) b0 = ep.bias[col];
-          if (col + 1 < N) b1 = ep.bias[col + 1];
-        }
-        const float s0 = (EPI == FACT_EPI_SPLIT && col < ep.scale_cols) ? ep.scale : 1.f;
-        const float s1 = (EPI == FACT_EPI_SPLIT && col + 1 < ep.scale_cols) ? ep.scale : 1.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = rr * 2 + (lane >> 4);
-          const int row = row_base + r;
-          if (row < M && col < N) {
-            float x0 = scratch[r * 33 + cp], x1 = scratch[r * 33 + cp + 1];
-            if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
-              x0 = gelu_tanh(x0 + b0);
-              x1 = gelu_tanh(x1 + b1);
-            } else {
-              x0 *= s0;
-              x1 *= s1;
-            }
-            bf16 h0, l0, h1, l1;
-            split_bf16(x0, h0, l0);
-            split_bf16(x1, h1, l1);
-            const size_t o = static_cast<size_t>(row) * ep.ldo + col;
-            if (col + 1 < N) {
-              *reinterpret_cast<uint32_t*>(ep.out_hi + o) = pack_bf16x2(h0, h1);
-              if (ep.out_lo) *reinterpret_cast<uint32_t*>(ep.out_lo + o) = pack_bf16x2(l0, l1);
-            } else {
-              ep.out_hi[o] = h0;
-              if (ep.out_lo) ep.out_lo[o] = l0;
-            }
-          }
-        }
+      for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* rrow = (EPI == FACT_EPI_BIAS_RESID_F32 && row_ok) ? ep.resid + static_cast<size_t>(row) * ep.ldr
+                                                                      : nullptr;
+      if (EPI == FACT_EPI_BIAS_RESID_F32 && ep.vec_ok && row_ok && n0 + half * 32 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = reinterpret_cast<const float4*>(rrow + n0 + half * 32)[i];
       }
+      mbar_wait(tmem_full_bar(acc), acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        const bool fast = ep.vec_ok && col0 + 32 <= N;
+        float4 rcur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
+        // next chunk's residual goes in flight before this chunk's stores
+        if (EPI == FACT_EPI_BIAS_RESID_F32 && c + 2 < BN / 32 && ep.vec_ok && row_ok && col0 + 64 + 32 <= N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rv[i] = reinterpret_cast<const float4*>(rrow + col0 + 64)[i];
+        }
+        epilogue_chunk<EPI>(v, rcur, row, col0, row_ok, fast, N, ep);
+      }
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
     }
   }
 
@@ -283,6 +359,16 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int 
   return FACT_OK;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int BN, int NPART, int STAGES, int EPI>
 static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                       int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
@@ -293,8 +379,10 @@ static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
     FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  dim3 grid((n + BN - 1) / BN, (m + BM - 1) / BM);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, ep);
+  const int tiles_n = (n + BN - 1) / BN, tiles_m = (m + BM - 1) / BM;
+  const int num_tiles = tiles_n * tiles_m;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, num_tiles, ep);
   FACT_LAUNCH_CHECK("gemm_tc_kernel launch");
   return FACT_OK;
 }
@@ -321,6 +409,8 @@ int gemm_tile_n(int n) {
   if (n % 256 == 0) return 256;  // 3072 = 12 x 256
   return 128;
 }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace fact
 
@@ -354,6 +444,12 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
   ep.seq_in = epi->seq_in;
   ep.seq_out = epi->seq_out;
   ep.seq_off = epi->seq_off;
+  if (split_out)
+    ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
+                (!ep.bias || aligned16(ep.bias));
+  else
+    ep.vec_ok = (ep.ldo % 4 == 0) && aligned16(ep.out_f32) && (!ep.bias || aligned16(ep.bias)) &&
+                (!ep.resid || ((ep.ldr % 4 == 0) && aligned16(ep.resid)));
 
   const int bn = gemm_tile_n(n);
   const bool precise = a_lo != nullptr;
@@ -374,7 +470,7 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
     if (bn == 256) return launch_epi<256, 2, 2>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
     return launch_epi<128, 2, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
   }
-  if (bn == 160) return launch_epi<160, 1, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+  if (bn == 160) return launch_epi<160, 1, 6>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
   if (bn == 256) return launch_epi<256, 1, 4>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
-  return launch_epi<128, 1, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+  return launch_epi<128, 1, 6>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
 }

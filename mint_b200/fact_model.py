@@ -186,9 +186,24 @@ class FACTModel:
         n = min(int(steps), audio_len - d.audio.seq_len + 1)   # the loop breaks on the first short window (:125-126)
         if n <= 0:
             raise ValueError("no full audio window: tf.concat of an empty list fails in the reference too")
-        hist = torch.empty((batch, d.motion.seq_len + n, d.motion.feature_dim), dtype=torch.float32,
-                           device=self.device)
-        hist[:, :d.motion.seq_len].copy_(motion)
+        hist = self.new_history(motion, n)
+        self.generate_into(hist, audio, 0, n)
+        return hist[:, d.motion.seq_len:].contiguous()
+
+    def new_history(self, motion_seed: torch.Tensor, capacity: int) -> torch.Tensor:
+        """[B, motion_seq + capacity, motion_dim] device buffer whose head is the seed; frames are appended in place."""
+        d = self.dims
+        motion_seed = self._to_dev(motion_seed, d.motion.feature_dim, "motion_input")
+        hist = torch.empty((motion_seed.shape[0], d.motion.seq_len + capacity, d.motion.feature_dim),
+                           dtype=torch.float32, device=self.device)
+        hist[:, :d.motion.seq_len].copy_(motion_seed)
+        return hist
+
+    def generate_into(self, hist: torch.Tensor, audio: torch.Tensor, start: int, n: int) -> None:
+        """Generate frames [start, start + n) into `hist` (device tensors; continues a previous call when start > 0)."""
+        d = self.dims
+        batch, audio_len = audio.shape[0], audio.shape[1]
+        capacity = hist.shape[1] - d.motion.seq_len
         ws, ws_bytes = self._workspace(batch)
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
@@ -199,14 +214,13 @@ class FACTModel:
                 run = self._side_stream
                 run.wait_stream(cur)
             lib.check(self._lib.fact_infer_auto_regressive(
-                C.byref(self._cdims), C.byref(self._cw), hist.data_ptr(), audio.data_ptr(), audio_len, batch, n,
-                self._step_counter.data_ptr(), ws, ws_bytes, lib.MODES[self.mode], 1 if self.use_graph else 0,
-                run.cuda_stream), "fact_infer_auto_regressive")
+                C.byref(self._cdims), C.byref(self._cw), hist.data_ptr(), capacity, audio.data_ptr(), audio_len,
+                batch, start, n, self._step_counter.data_ptr(), ws, ws_bytes, lib.MODES[self.mode],
+                1 if self.use_graph else 0, run.cuda_stream), "fact_infer_auto_regressive")
             if run is not cur:
                 cur.wait_stream(run)
-                for t in (hist, audio, motion):
+                for t in (hist, audio):
                     t.record_stream(run)
-        return hist[:, d.motion.seq_len:].contiguous()
 
     def loss(self, target, pred) -> torch.Tensor:
         """L2 motion generation loss on the first target_seq_len frames (fact_model.py:134-148)."""
