@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=4, help="clips per step of the CPU baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / fast-mode legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg only")
+    ap.add_argument("--kernels-only", action="store_true", help="developer aid: time the hot kernels alone and exit")
     return ap.parse_args()
 
 
@@ -278,6 +279,12 @@ def run_ours(args):
     audio_h = torch.randn(B, T, dims.audio.feature_dim, generator=gen).pin_memory()
 
     stream = torch.cuda.Stream(dev)
+    if args.kernels_only:
+        with torch.cuda.stream(stream):
+            kr = kernel_rooflines(model, args.batch, args.mode, peaks, stream)
+        for k, v in kr.items():
+            print(k, {kk: round(vv, 6) for kk, vv in v.items()})
+        return
 
     def barrier():
         torch.cuda.synchronize(dev)

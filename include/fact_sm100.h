@@ -153,6 +153,9 @@ FACT_API int fact_gemm_f32(const float* a, int lda, const float* w_keras, int m,
 FACT_API int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
               int head_dim, void* stream);
 
+/* Developer switches. "sdpa_legacy" = 1 forces the generic mma.sync attention kernel instead of the tcgen05 one. */
+FACT_API int fact_set_flag(const char* name, int value);
+
 /* LinearEmbedding + PositionEmbedding (fact_model.py:88-90,94-95; base_models.py:135,156):
  * y[b*n_tok + t, :] = x[b, start + t, :f] . W[f, d] + bias + pos[t, :],  start = step_ptr ? *step_ptr : 0.
  * x is [batch, x_len, f] with batch stride x_batch_stride elements. */

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the translation units of libfact_sm100.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -30,6 +31,9 @@ int cuda_fail(cudaError_t e, const char* what);
       return (code);                  \
     }                                 \
   } while (0)
+
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols);
+int num_sms();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

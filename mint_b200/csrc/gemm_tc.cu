@@ -317,24 +317,28 @@ static EncodeTiledFn get_encode_fn() {
 
 struct TmapKey {
   const void* ptr;
-  int rows, cols, ld, box_rows;
+  int rows, cols, ld, box_rows, box_cols;
   bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols;
   }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) ^ (static_cast<size_t>(k.cols) << 20) ^
-         (static_cast<size_t>(k.ld) << 40) ^ (static_cast<size_t>(k.box_rows) << 52);
+         (static_cast<size_t>(k.ld) << 40) ^ (static_cast<size_t>(k.box_rows) << 52) ^
+         (static_cast<size_t>(k.box_cols) << 8);
     return h;
   }
 };
 
-// bf16 row-major [rows, cols] with row pitch ld elements -> 2-D tiled map, box {64 cols, box_rows}, 128B swizzle.
-static int make_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows) {
+// bf16 row-major [rows, cols] with row pitch ld elements -> 2-D tiled map, box {box_cols, box_rows}; the swizzle
+// span equals the box width (64 cols -> SWIZZLE_128B, 16 cols -> SWIZZLE_32B).
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, rows, cols, ld, box_rows};
+  TmapKey key{ptr, rows, cols, ld, box_rows, box_cols};
+  FACT_REQUIRE(box_cols == 64 || box_cols == 16, FACT_ERR_UNSUPPORTED, "tensor-map box width %d", box_cols);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -347,10 +351,11 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int 
                "TMA row pitch (%d bf16) must be a multiple of 16 bytes", ld);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FACT_REQUIRE(r == CUDA_SUCCESS, FACT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%d",
                static_cast<int>(r), rows, cols, ld, box_rows);
@@ -359,7 +364,7 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int 
   return FACT_OK;
 }
 
-static int num_sms() {
+int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -455,11 +460,11 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
   const bool precise = a_lo != nullptr;
   CUtensorMap a0, a1, b0, b1;
   int rc;
-  if ((rc = make_tmap(&a0, a_hi, m, k, lda, BM))) return rc;
-  if ((rc = make_tmap(&b0, w_hi, n, k, ldw, bn))) return rc;
+  if ((rc = make_tmap_bf16(&a0, a_hi, m, k, lda, BM, BK))) return rc;
+  if ((rc = make_tmap_bf16(&b0, w_hi, n, k, ldw, bn, BK))) return rc;
   if (precise) {
-    if ((rc = make_tmap(&a1, a_lo, m, k, lda, BM))) return rc;
-    if ((rc = make_tmap(&b1, w_lo, n, k, ldw, bn))) return rc;
+    if ((rc = make_tmap_bf16(&a1, a_lo, m, k, lda, BM, BK))) return rc;
+    if ((rc = make_tmap_bf16(&b1, w_lo, n, k, ldw, bn, BK))) return rc;
   } else {
     a1 = a0;
     b1 = b0;

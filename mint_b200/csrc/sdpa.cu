@@ -8,6 +8,8 @@
 // Precise mode (NPART == 2): q, k, v, p are hi+lo bf16 pairs and every product is hi.hi + lo.hi + hi.lo.
 // Sequence lengths here are 120 / 240 / 360 (not multiples of 64): tail keys are masked to -inf, tail query
 // rows are computed on zero inputs and never stored.
+#include <string.h>
+
 #include "fact_internal.h"
 #include "fact_ptx.cuh"
 
@@ -104,23 +106,35 @@ sdpa_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, bf
 #pragma unroll
     for (int i = 0; i < SDPA_KB / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
     {
+      // products are issued tile-major (8 independent accumulators between two updates of the same tile), so the
+      // hi.hi / lo.hi / hi.lo passes never wait on each other's HMMA latency
       const int mat = lane >> 3, r = lane & 7;
 #pragma unroll
       for (int ks = 0; ks < KSTEPS; ++ks) {
+        uint32_t kh[SDPA_KB / 16][4], kl[SDPA_KB / 16][4];
+        const int col = ks * 16 + (mat & 1) * 8;
 #pragma unroll
         for (int ntp = 0; ntp < SDPA_KB / 16; ++ntp) {
           const int krow = ntp * 16 + (mat >> 1) * 8 + r;
-          const int col = ks * 16 + (mat & 1) * 8;
-          uint32_t b00, b01, b10, b11;
-          ldsm_x4(smem_u32(Ks + krow * DHP + col), b00, b01, b10, b11);
-          mma_bf16_16816(s[2 * ntp], qf[0][ks], b00, b01);
-          mma_bf16_16816(s[2 * ntp + 1], qf[0][ks], b10, b11);
-          if (NPART == 2) {
-            mma_bf16_16816(s[2 * ntp], qf[NPART - 1][ks], b00, b01);       // q_lo . k_hi
-            mma_bf16_16816(s[2 * ntp + 1], qf[NPART - 1][ks], b10, b11);
-            ldsm_x4(smem_u32(Ks + TILE + krow * DHP + col), b00, b01, b10, b11);
-            mma_bf16_16816(s[2 * ntp], qf[0][ks], b00, b01);               // q_hi . k_lo
-            mma_bf16_16816(s[2 * ntp + 1], qf[0][ks], b10, b11);
+          ldsm_x4(smem_u32(Ks + krow * DHP + col), kh[ntp][0], kh[ntp][1], kh[ntp][2], kh[ntp][3]);
+          if (NPART == 2)
+            ldsm_x4(smem_u32(Ks + TILE + krow * DHP + col), kl[ntp][0], kl[ntp][1], kl[ntp][2], kl[ntp][3]);
+        }
+#pragma unroll
+        for (int ntp = 0; ntp < SDPA_KB / 16; ++ntp) {
+          mma_bf16_16816(s[2 * ntp], qf[0][ks], kh[ntp][0], kh[ntp][1]);
+          mma_bf16_16816(s[2 * ntp + 1], qf[0][ks], kh[ntp][2], kh[ntp][3]);
+        }
+        if (NPART == 2) {
+#pragma unroll
+          for (int ntp = 0; ntp < SDPA_KB / 16; ++ntp) {  // q_lo . k_hi
+            mma_bf16_16816(s[2 * ntp], qf[NPART - 1][ks], kh[ntp][0], kh[ntp][1]);
+            mma_bf16_16816(s[2 * ntp + 1], qf[NPART - 1][ks], kh[ntp][2], kh[ntp][3]);
+          }
+#pragma unroll
+          for (int ntp = 0; ntp < SDPA_KB / 16; ++ntp) {  // q_hi . k_lo
+            mma_bf16_16816(s[2 * ntp], qf[0][ks], kl[ntp][0], kl[ntp][1]);
+            mma_bf16_16816(s[2 * ntp + 1], qf[0][ks], kl[ntp][2], kl[ntp][3]);
           }
         }
       }
@@ -180,18 +194,26 @@ sdpa_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, bf
           al[i] = pack_bf16x2(l0, l1);
         }
         const int vrow = kk * 16 + (mat & 1) * 8 + r;
+        uint32_t vh[DT / 2][4];
 #pragma unroll
         for (int dtp = 0; dtp < DT / 2; ++dtp) {
           const int col = (2 * dtp + (mat >> 1)) * 8;
-          uint32_t b00, b01, b10, b11;
-          ldsm_x4_t(smem_u32(Vs + vrow * DHP + col), b00, b01, b10, b11);
-          mma_bf16_16816(o[2 * dtp], ah, b00, b01);
-          mma_bf16_16816(o[2 * dtp + 1], ah, b10, b11);
-          if (NPART == 2) {
-            mma_bf16_16816(o[2 * dtp], al, b00, b01);       // p_lo . v_hi
-            mma_bf16_16816(o[2 * dtp + 1], al, b10, b11);
+          ldsm_x4_t(smem_u32(Vs + vrow * DHP + col), vh[dtp][0], vh[dtp][1], vh[dtp][2], vh[dtp][3]);
+          mma_bf16_16816(o[2 * dtp], ah, vh[dtp][0], vh[dtp][1]);
+          mma_bf16_16816(o[2 * dtp + 1], ah, vh[dtp][2], vh[dtp][3]);
+        }
+        if (NPART == 2) {
+#pragma unroll
+          for (int dtp = 0; dtp < DT / 2; ++dtp) {  // p_lo . v_hi
+            mma_bf16_16816(o[2 * dtp], al, vh[dtp][0], vh[dtp][1]);
+            mma_bf16_16816(o[2 * dtp + 1], al, vh[dtp][2], vh[dtp][3]);
+          }
+#pragma unroll
+          for (int dtp = 0; dtp < DT / 2; ++dtp) {  // p_hi . v_lo
+            const int col = (2 * dtp + (mat >> 1)) * 8;
+            uint32_t b00, b01, b10, b11;
             ldsm_x4_t(smem_u32(Vs + TILE + vrow * DHP + col), b00, b01, b10, b11);
-            mma_bf16_16816(o[2 * dtp], ah, b00, b01);       // p_hi . v_lo
+            mma_bf16_16816(o[2 * dtp], ah, b00, b01);
             mma_bf16_16816(o[2 * dtp + 1], ah, b10, b11);
           }
         }
@@ -240,9 +262,22 @@ static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int b
   return FACT_OK;
 }
 
+int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
+                cudaStream_t st);
+int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
+
 }  // namespace fact
 
 using namespace fact;
+
+extern "C" int fact_set_flag(const char* name, int value) {
+  if (name && strcmp(name, "sdpa_legacy") == 0) {
+    g_sdpa_legacy = value;
+    return FACT_OK;
+  }
+  set_error("fact_set_flag: unknown flag %s", name ? name : "(null)");
+  return FACT_ERR_UNSUPPORTED;
+}
 
 extern "C" int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n,
                          int heads, int head_dim, void* stream) {
@@ -257,6 +292,10 @@ extern "C" int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, v
   bf16* ol = static_cast<bf16*>(out_lo);
   cudaStream_t st = as_stream(stream);
   const bool precise = qkv_lo != nullptr;
+  if (!g_sdpa_legacy) {  // B200-native path: tcgen05 + TMEM-resident scores (head_dim 80, n <= 384)
+    const int rc = sdpa_tc_try(qh, ql, oh, ol, batch, n, heads, head_dim, st);
+    if (rc != FACT_ERR_UNSUPPORTED) return rc;
+  }
 #define FACT_SDPA_CASE(DHV)                                                            \
   case DHV:                                                                            \
     return precise ? launch_sdpa<DHV, 2>(qh, ql, oh, ol, batch, n, heads, st)          \

@@ -1,0 +1,315 @@
+// tcgen05 attention core for the FACT sequence lengths (N <= 384, head_dim 80); reference math:
+// mint/core/base_models.py:76-86 (softmax(q.k^T * d_model^-0.5) . v, no mask, heads merged "b h n d -> b n (h d)").
+//
+// B200 mapping (persistent, one CTA per SM, a tile = one (batch, head, 128-query block)):
+//   * the whole score block lives in TMEM: S[128 x 384] fp32 (384 columns) + O[128 x 80] fp32 (80 columns) <= 512;
+//     row i of the tile is TMEM lane i, so the softmax is thread-local (no shuffles, no online rescaling);
+//   * S = Q.K^T and O = P.V are tcgen05.mma (UMMA 128 x 128 x 16 and 128 x 80 x 16) issued by one thread; in precise
+//     mode each product is hi.hi + lo.hi + hi.lo accumulated in the same TMEM tile;
+//   * P is written back IN PLACE over S (32 fp32 columns -> 16 columns bf16 P_hi | 16 columns bf16 P_lo) with
+//     tcgen05.st and consumed by the PV MMA as a TMEM A-operand -- probabilities never touch shared or global memory;
+//   * Q/K/V head slices arrive by TMA as [rows][16]-element sub-tiles (SWIZZLE_32B; 80 = 5 x 16 so no padding);
+//     K sub-tiles are K-major B operands, V sub-tiles are MN-major B operands of the PV product;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = softmax + output (TMEM lane quadrant = warp % 4).
+// Keys beyond N inside the last 128-key block are other rows of the qkv buffer (or TMA zero fill): their scores are
+// never read and their probabilities are written as exact zeros.
+#include "fact_internal.h"
+#include "fact_ptx.cuh"
+
+namespace fact {
+
+constexpr int TC_QB = 128;           // query rows per tile (UMMA M)
+constexpr int TC_KB = 128;           // keys per block (UMMA N of the score MMA)
+constexpr int TC_MAXBLK = 3;         // N <= 384
+constexpr int TC_DH = 80;
+constexpr int TC_KS = TC_DH / 16;    // 16-wide head_dim slices
+constexpr int TC_SUB = TC_KB * 32;   // bytes of one [128 rows][16 el] sub-tile
+constexpr int TC_KV_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_O_COL = TC_MAXBLK * TC_KB;  // 384
+constexpr int TC_TMEM_COLS = 512;
+
+template <int NPART>
+struct SdpaTcCfg {
+  static constexpr int PART_BYTES = TC_KS * TC_SUB;          // 20 KB: one 128 x 80 operand part
+  static constexpr int TILE_BYTES = NPART * PART_BYTES;      // Q tile or one K / V block
+  static constexpr int BAR_OFF = (1 + TC_KV_STAGES) * TILE_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + BAR_OFF + 256;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+};
+
+template <int NPART>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, int N, int H, int q_blocks, int num_tiles) {
+  using Cfg = SdpaTcCfg<NPART>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base;
+  auto kv_smem = [&](int s) { return smem_base + (1 + s) * Cfg::TILE_BYTES; };
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFF;
+  // barriers: kv_full[4] kv_empty[4] q_full q_empty s_full[3] p_full[3] o_full o_empty | tmem_ptr
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (TC_KV_STAGES + s); };
+  const uint32_t q_full = bar_base + 8u * (2 * TC_KV_STAGES);
+  const uint32_t q_empty = q_full + 8;
+  auto s_full = [&](int c) { return q_full + 16u + 8u * c; };
+  auto p_full = [&](int c) { return q_full + 16u + 8u * (TC_MAXBLK + c); };
+  const uint32_t o_full = q_full + 16u + 8u * (2 * TC_MAXBLK);
+  const uint32_t o_empty = o_full + 8;
+  const uint32_t tmem_ptr_addr = o_empty + 8;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + Cfg::BAR_OFF + 8 * (2 * TC_KV_STAGES) + 16 + 8 * (2 * TC_MAXBLK) + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * TC_DH;
+  const int nblk = (N + TC_KB - 1) / TC_KB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_hi);
+    if (NPART == 2) tma_prefetch_desc(&tm_lo);
+    for (int s = 0; s < TC_KV_STAGES; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int c = 0; c < TC_MAXBLK; ++c) {
+      mbar_init(s_full(c), 1);
+      mbar_init(p_full(c), 4);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr_addr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  auto tile_coords = [&](int tile, int& b, int& h, int& qb) {
+    qb = tile % q_blocks;
+    const int bh = tile / q_blocks;
+    h = bh % H;
+    b = bh / H;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {  // ------------------------------------------------------------ TMA producer
+      uint32_t it = 0, t = 0;
+      auto load_block = [&](uint32_t dst, uint32_t bar, int col, int row) {
+        mbar_arrive_expect_tx(bar, Cfg::TILE_BYTES);
+        for (int ks = 0; ks < TC_KS; ++ks) {
+          tma_load_2d(dst + ks * TC_SUB, &tm_hi, col + ks * 16, row, bar);
+          if (NPART == 2) tma_load_2d(dst + Cfg::PART_BYTES + ks * TC_SUB, &tm_lo, col + ks * 16, row, bar);
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        int b, h, qb;
+        tile_coords(tile, b, h, qb);
+        const int row0 = b * N;
+        mbar_wait(q_empty, (t & 1) ^ 1);
+        load_block(q_smem, q_full, h * TC_DH, row0 + qb * TC_QB);
+        for (int which = 1; which <= 2; ++which)      // all K blocks, then all V blocks
+          for (int c = 0; c < nblk; ++c, ++it) {
+            const int s = it % TC_KV_STAGES;
+            mbar_wait(kv_empty(s), ((it / TC_KV_STAGES) & 1) ^ 1);
+            load_block(kv_smem(s), kv_full(s), which * D + h * TC_DH, row0 + c * TC_KB);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32_ex(TC_QB, TC_KB, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_f32_ex(TC_QB, TC_DH, 1);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t tph = t & 1;
+        mbar_wait(q_full, tph);
+        tc_fence_after();
+        // ---- S[:, 128c : 128c+128] = Q . K_c^T
+        for (int c = 0; c < nblk; ++c, ++it) {
+          const int s = it % TC_KV_STAGES;
+          mbar_wait(kv_full(s), (it / TC_KV_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + c * TC_KB;
+#pragma unroll
+          for (int ks = 0; ks < TC_KS; ++ks) {
+            const uint64_t qh = umma_desc_k_sw32(q_smem + ks * TC_SUB);
+            const uint64_t kh = umma_desc_k_sw32(kv_smem(s) + ks * TC_SUB);
+            umma_bf16(d, qh, kh, idesc_s, ks > 0 ? 1u : 0u);
+            if (NPART == 2) {
+              const uint64_t ql = umma_desc_k_sw32(q_smem + Cfg::PART_BYTES + ks * TC_SUB);
+              const uint64_t kl = umma_desc_k_sw32(kv_smem(s) + Cfg::PART_BYTES + ks * TC_SUB);
+              umma_bf16(d, ql, kh, idesc_s, 1u);
+              umma_bf16(d, qh, kl, idesc_s, 1u);
+            }
+          }
+          umma_commit(kv_empty(s));
+          umma_commit(s_full(c));
+        }
+        umma_commit(q_empty);  // Q tile reusable once every score MMA has read it
+        // ---- O = sum_c P_c . V_c   (P from TMEM, V MN-major from shared)
+        for (int c = 0; c < nblk; ++c, ++it) {
+          const int s = it % TC_KV_STAGES;
+          mbar_wait(kv_full(s), (it / TC_KV_STAGES) & 1);
+          mbar_wait(p_full(c), tph);
+          if (c == 0) mbar_wait(o_empty, tph ^ 1);  // previous tile's output has been read out of TMEM
+          tc_fence_after();
+          const int nvalid = min(TC_KB, N - c * TC_KB);
+          const int ksteps = (nvalid + 15) >> 4;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint32_t a_hi = tmem_base + c * TC_KB + 32 * (j >> 1) + 8 * (j & 1);
+            const uint64_t vh = umma_desc_mn_sw32(kv_smem(s) + j * 512, TC_SUB, 256);
+            umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vh, idesc_o, (c > 0 || j > 0) ? 1u : 0u);
+            if (NPART == 2) {
+              const uint64_t vl = umma_desc_mn_sw32(kv_smem(s) + Cfg::PART_BYTES + j * 512, TC_SUB, 256);
+              umma_bf16_ts(tmem_base + TC_O_COL, a_hi + 16, vh, idesc_o, 1u);
+              umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vl, idesc_o, 1u);
+            }
+          }
+          umma_commit(kv_empty(s));
+        }
+        umma_commit(o_full);
+      }
+    }
+  } else {  // ------------------------------------------------------------------------ softmax + output warps 2..5
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const uint32_t tph = t & 1;
+      int b, h, qb;
+      tile_coords(tile, b, h, qb);
+      const int row = qb * TC_QB + q * 32 + lane;
+      // ---- pass 1: row max over the valid keys (scores are already in the exp2 domain)
+      float mx = -INFINITY;
+      for (int c = 0; c < nblk; ++c) {
+        mbar_wait(s_full(c), tph);
+        tc_fence_after();
+        const int nvalid = min(TC_KB, N - c * TC_KB);
+        for (int g = 0; g * 32 < nvalid; ++g) {
+          float v[32];
+          tmem_ld_32x32(lane_base + c * TC_KB + g * 32, v);
+          tmem_ld_wait();
+          const int lim = nvalid - g * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < lim ? v[i] : -INFINITY);
+        }
+      }
+      // ---- pass 2: p = 2^(s - max); P_hi | P_lo overwrite the score columns they came from
+      float lsum = 0.f;
+      for (int c = 0; c < nblk; ++c) {
+        const int nvalid = min(TC_KB, N - c * TC_KB);
+        for (int g = 0; g * 32 < nvalid; ++g) {
+          float v[32];
+          const uint32_t addr = lane_base + c * TC_KB + g * 32;
+          tmem_ld_32x32(addr, v);
+          tmem_ld_wait();
+          const int lim = nvalid - g * 32;
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = (2 * i < lim) ? ex2_approx(v[2 * i] - mx) : 0.f;
+            const float p1 = (2 * i + 1 < lim) ? ex2_approx(v[2 * i + 1] - mx) : 0.f;
+            lsum += p0 + p1;
+            const uint32_t hp = cvt_bf16x2(p0, p1);
+            pk[i] = hp;
+            if (NPART == 2) {
+              const float h0 = __uint_as_float(hp << 16), h1 = __uint_as_float(hp & 0xffff0000u);
+              pk[16 + i] = cvt_bf16x2(p0 - h0, p1 - h1);
+            }
+          }
+          if (NPART == 2) tmem_st_32x32(addr, pk);
+          else tmem_st_32x16(addr, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(c));
+      }
+      // ---- output: O / l, split, "b h n d -> b n (h d)"
+      const float inv = 1.f / lsum;
+      mbar_wait(o_full, tph);
+      tc_fence_after();
+      float ov[TC_DH];
+      tmem_ld_32x32(lane_base + TC_O_COL, ov);
+      tmem_ld_32x32(lane_base + TC_O_COL + 32, ov + 32);
+      tmem_ld_32x16(lane_base + TC_O_COL + 64, ov + 64);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (row < N) {
+        const size_t base = (static_cast<size_t>(b) * N + row) * D + h * TC_DH;
+        uint32_t hh[TC_DH / 2], ll[TC_DH / 2];
+#pragma unroll
+        for (int i = 0; i < TC_DH / 2; ++i) {
+          const float x0 = ov[2 * i] * inv, x1 = ov[2 * i + 1] * inv;
+          const uint32_t hp = cvt_bf16x2(x0, x1);
+          hh[i] = hp;
+          ll[i] = cvt_bf16x2(x0 - __uint_as_float(hp << 16), x1 - __uint_as_float(hp & 0xffff0000u));
+        }
+        uint4* ph = reinterpret_cast<uint4*>(o_hi + base);
+#pragma unroll
+        for (int i = 0; i < TC_DH / 8; ++i) ph[i] = make_uint4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
+        if (NPART == 2) {
+          uint4* pl = reinterpret_cast<uint4*>(o_lo + base);
+#pragma unroll
+          for (int i = 0; i < TC_DH / 8; ++i)
+            pl[i] = make_uint4(ll[4 * i], ll[4 * i + 1], ll[4 * i + 2], ll[4 * i + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int NPART>
+static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads,
+                          cudaStream_t st) {
+  using Cfg = SdpaTcCfg<NPART>;
+  auto kern = sdpa_tc_kernel<NPART>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int d = heads * TC_DH;
+  CUtensorMap tmh, tml;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmh, qh, batch * n, 3 * d, 3 * d, TC_KB, 16))) return rc;
+  if (NPART == 2) {
+    if ((rc = make_tmap_bf16(&tml, ql, batch * n, 3 * d, 3 * d, TC_KB, 16))) return rc;
+  } else {
+    tml = tmh;
+  }
+  const int q_blocks = (n + TC_QB - 1) / TC_QB;
+  const int num_tiles = q_blocks * heads * batch;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmh, tml, oh, ol, n, heads, q_blocks, num_tiles);
+  FACT_LAUNCH_CHECK("sdpa_tc_kernel launch");
+  return FACT_OK;
+}
+
+// tcgen05 path: head_dim 80, n <= 384, 16-byte aligned buffers.  Returns FACT_ERR_UNSUPPORTED (without setting an
+// error) when the shape is outside that envelope so that fact_sdpa falls back to the generic mma.sync kernel.
+int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
+                cudaStream_t st) {
+  if (head_dim != TC_DH || n > TC_MAXBLK * TC_KB) return FACT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qh) | reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ql) |
+       reinterpret_cast<uintptr_t>(ol)) & 15)
+    return FACT_ERR_UNSUPPORTED;
+  return ql ? launch_sdpa_tc<2>(qh, ql, oh, ol, batch, n, heads, st)
+            : launch_sdpa_tc<1>(qh, ql, oh, ol, batch, n, heads, st);
+}
+
+}  // namespace fact

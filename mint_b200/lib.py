@@ -52,6 +52,7 @@ SIGNATURES = {
     "fact_gemm": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp]),
     "fact_gemm_f32": (_i, [_vp, _i, _vp, _i, _i, _i, C.POINTER(GemmEpilogue), _vp]),
     "fact_sdpa": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fact_set_flag": (_i, [C.c_char_p, _i]),
     "fact_embed": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fact_head_rows": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _i, _i, _i, _vp]),
     "fact_mse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -176,10 +176,23 @@ def test_gemm_f32(fact_lib, cuda, kind):
     assert rel_err(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("legacy", [0, 1])
 @pytest.mark.parametrize("precise", [True, False])
 @pytest.mark.parametrize("batch,n,heads,dh", [(2, 120, 10, 80), (1, 240, 10, 80), (2, 360, 10, 80), (3, 37, 2, 16),
-                                              (1, 128, 3, 64), (1, 65, 4, 32)])
-def test_sdpa(fact_lib, cuda, batch, n, heads, dh, precise):
+                                              (1, 128, 3, 64), (1, 65, 4, 32), (5, 384, 2, 80), (40, 360, 10, 80),
+                                              (2, 7, 1, 80)])
+def test_sdpa(fact_lib, cuda, batch, n, heads, dh, precise, legacy):
+    """legacy=0: tcgen05 kernel where the shape allows (dh 80, n <= 384), else mma.sync; legacy=1: always mma.sync."""
+    if legacy and dh != 80:
+        pytest.skip("already the mma.sync path")
+    fact_lib.fact_set_flag(b"sdpa_legacy", legacy)
+    try:
+        _sdpa_case(fact_lib, cuda, batch, n, heads, dh, precise)
+    finally:
+        fact_lib.fact_set_flag(b"sdpa_legacy", 0)
+
+
+def _sdpa_case(fact_lib, cuda, batch, n, heads, dh, precise):
     d = heads * dh
     g = torch.Generator(device="cpu").manual_seed(5)
     qkv = torch.randn(batch * n, 3 * d, generator=g).to(cuda)
@@ -194,6 +207,7 @@ def test_sdpa(fact_lib, cuda, batch, n, heads, dh, precise):
     s = q @ k.transpose(-1, -2)                       # log2 domain
     p = torch.softmax(s * math.log(2.0), dim=-1)
     ref = (p @ v).permute(0, 2, 1, 3).reshape(batch * n, d)
+    torch.cuda.synchronize()
     got = join(o_hi, o_lo if precise else None).double()
     tol = 5e-5 if precise else 2e-2   # bf16 mode rounds p and the output to 8 bits
     assert (got - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), float((got - ref).abs().max())
