@@ -343,17 +343,22 @@ def run_ours(args):
                                  for k, v in kr.items()}
             # per-frame launch counts of each GEMM at the cross-modal shape (encoder shapes are smaller)
             dom = max(("gemm_qkv", "gemm_out", "gemm_ff1", "gemm_ff2"), key=lambda k: kr[k]["s"])
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+            if args.mode == "precise" and B == 128 and os.path.exists(tpath):
+                with open(tpath) as f:
+                    traffic = json.load(f).get(dom)
             extras["roofline"] = {
                 "bound": "tensor", "kernel": f"gemm_tc_kernel ({dom}, M={B * dims.cross_seq})",
                 "achieved": kr[dom]["executed_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": kr[dom]["executed_tflops"] / peaks["bf16_tflops"], "traffic": None,
+                "frac": kr[dom]["executed_tflops"] / peaks["bf16_tflops"], "traffic": traffic,
                 "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                 "algorithmic_tflops": kr[dom]["algo_tflops"],
                 "note": ("executed = bf16 tensor FLOPs issued (3 MMAs per product in precise mode); "
                          "algorithmic = 2*M*N*K of the fp32-grade product") if args.mode == "precise" else "bf16",
             }
             extras["attn_roofline"] = {
-                "bound": "hbm", "kernel": "attention block = LN+split, QKV GEMM, sdpa_kernel, out-proj GEMM",
+                "bound": "hbm", "kernel": "attention block = ln_split_kernel, gemm_tc_kernel (QKV), sdpa_tc_kernel, gemm_tc_kernel (out-proj)",
                 "achieved": kr["attn_block"]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": kr["attn_block"]["frac_hbm"],
                 "sdpa_core_gbs": kr["sdpa"]["gbs"], "sdpa_core_frac": kr["sdpa"]["gbs"] / peaks["hbm_gbs"],

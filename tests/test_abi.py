@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports exactly what include/fact_sm100.h declares (no compute calls: CPU-only)."""
+import ctypes
+import os
+import re
+
+from mint_b200 import lib as L
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "fact_sm100.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"FACT_API\s+[\w\s\*]+?\b(fact_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_hot_path_entry_points():
+    names = _declared()
+    for must in ("fact_forward", "fact_infer_auto_regressive", "fact_gemm", "fact_sdpa", "fact_layernorm_split",
+                 "fact_embed", "fact_head_rows", "fact_mse", "fact_pack_weight", "fact_workspace_bytes"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(fact_lib):
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for name in _declared():
+        assert hasattr(raw, name), f"{name} declared in fact_sm100.h but not exported"
+
+
+def test_ctypes_table_covers_the_header(fact_lib):
+    from mint_b200 import lib_bwd
+    bound = set(L.SIGNATURES) | set(lib_bwd.SIGNATURES)
+    assert set(_declared()) == bound
+
+
+def test_abi_version_and_error_string(fact_lib):
+    assert fact_lib.fact_abi_version() == 1
+    assert fact_lib.fact_set_flag(b"no_such_flag", 1) == -5
+    assert b"unknown flag" in fact_lib.fact_last_error()
+    d = L.Dims(800, 10, 3072, 2, 2, 12, 120, 240, 225, 35, 225)
+    need = fact_lib.fact_workspace_bytes(ctypes.byref(d), 128, L.MODE_PRECISE)
+    assert 1.0e9 < need < 2.5e9          # ~1.6 GB of activations at batch 128
+    assert fact_lib.fact_workspace_bytes(ctypes.byref(d), 128, L.MODE_BF16) < need
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    try:
+        L.load()
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("load() must raise when the CUDA library is absent")
