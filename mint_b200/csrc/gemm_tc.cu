@@ -297,6 +297,188 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------- CTA-pair variant
+// cta_group::2: a cluster of two CTAs (one TPC) computes a 256 x BN tile.  CTA r stages A rows [128 r, 128 r + 128)
+// and W rows [BN/2 r, BN/2 r + BN/2); the leader's single thread issues tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16)
+// which reads both CTAs' shared memory and writes each CTA's half of the accumulator into that CTA's TMEM.  Per SM and
+// K block this stages A + W/2 instead of A + W: the measured TMA ingest limit (~64 B/cycle/SM) stops binding.
+// Barriers: full[] and tmem_empty[] are the LEADER's (peer arrives remotely, peer TMA credits the leader's barrier);
+// empty[] and tmem_full[] exist in both CTAs and are signalled by multicast tcgen05.commit.
+template <int BN, int NPART, int STAGES>
+struct Gemm2Cfg {
+  static constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = NPART * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int ACC_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
+                                   : ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=256 / 32-column epilogue chunks");
+  static_assert((BN / 2) % 8 == 0, "W half must be whole 8-row swizzle atoms");
+  static_assert(ACC_COLS <= 512, "TMEM has 512 columns");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+  static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier block too small");
+};
+
+template <int BN, int NPART, int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_tc2_kernel(
+    const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, int M, int N, int K,
+    int tiles_n, int num_tiles, EpiArgs ep) {
+  using Cfg = Gemm2Cfg<BN, NPART, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (NPART == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // leader's arrive.expect_tx + peer's remote arrive
+      mbar_init(empty_bar(s), 1);  // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 2 * EPI_WARPS);  // both CTAs' epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr_addr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  auto sA = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + part * A_TILE_BYTES; };
+  auto sB = [&](int s, int part) {
+    return smem_base + s * Cfg::STAGE_BYTES + NPART * A_TILE_BYTES + part * Cfg::B_TILE_BYTES;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer (both CTAs)
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / tiles_n) * (2 * BM) + rank * BM;
+        const int n0 = (tile % tiles_n) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_leader(full_bar(s));
+          tma_load_2d_2sm(sA(s, 0), &tmA0, kb * BK, m0, full_bar(s));
+          tma_load_2d_2sm(sB(s, 0), &tmB0, kb * BK, n0, full_bar(s));
+          if (NPART == 2) {
+            tma_load_2d_2sm(sA(s, 1), &tmA1, kb * BK, m0, full_bar(s));
+            tma_load_2d_2sm(sB(s, 1), &tmB1, kb * BK, n0, full_bar(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {  // ---------------- MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
+      uint32_t it = 0, t = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint32_t koff = kk * UMMA_K * 2;
+            const uint64_t a_hi = umma_desc_k_sw128(sA(s, 0) + koff);
+            const uint64_t b_hi = umma_desc_k_sw128(sB(s, 0) + koff);
+            umma_bf16_2sm(tmem_d, a_hi, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            if (NPART == 2) {
+              const uint64_t a_lo = umma_desc_k_sw128(sA(s, 1) + koff);
+              const uint64_t b_lo = umma_desc_k_sw128(sB(s, 1) + koff);
+              umma_bf16_2sm(tmem_d, a_lo, b_hi, idesc, 1u);
+              umma_bf16_2sm(tmem_d, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          umma_commit_2sm(empty_bar(s), 0x3);  // both CTAs' stage s is free
+        }
+        umma_commit_2sm(tmem_full_bar(acc), 0x3);
+      }
+    }
+  } else {  // ---------------- epilogue warps (both CTAs): this CTA's 128 rows of the pair tile
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint32_t t = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      const int m0 = (tile / tiles_n) * (2 * BM) + rank * BM, n0 = (tile % tiles_n) * BN;
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      float4 rv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* rrow = (EPI == FACT_EPI_BIAS_RESID_F32 && row_ok) ? ep.resid + static_cast<size_t>(row) * ep.ldr
+                                                                      : nullptr;
+      if (EPI == FACT_EPI_BIAS_RESID_F32 && ep.vec_ok && row_ok && n0 + half * 32 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = reinterpret_cast<const float4*>(rrow + n0 + half * 32)[i];
+      }
+      mbar_wait(tmem_full_bar(acc), acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        const bool fast = ep.vec_ok && col0 + 32 <= N;
+        float4 rcur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
+        if (EPI == FACT_EPI_BIAS_RESID_F32 && c + 2 < BN / 32 && ep.vec_ok && row_ok && col0 + 64 + 32 <= N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rv[i] = reinterpret_cast<const float4*>(rrow + col0 + 64)[i];
+        }
+        epilogue_chunk<EPI>(v, rcur, row, col0, row_ok, fast, N, ep);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tmem_empty_bar(acc));
+        else mbar_arrive_leader(tmem_empty_bar(acc));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody frees TMEM / exits while the peer may still touch this CTA's barriers or TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -392,6 +574,42 @@ static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   return FACT_OK;
 }
 
+template <int BN, int NPART, int STAGES, int EPI>
+static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+                       int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN, NPART, STAGES>;
+  auto kern = gemm_tc2_kernel<BN, NPART, STAGES, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles_n = (n + BN - 1) / BN, tiles_m = (m + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = tiles_n * tiles_m;
+  int clusters = num_sms() / 2;
+  if (num_tiles < clusters) clusters = num_tiles;
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, num_tiles, ep);
+  FACT_LAUNCH_CHECK("gemm_tc2_kernel launch");
+  return FACT_OK;
+}
+
+template <int BN, int NPART, int STAGES>
+static int launch_epi2(int kind, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                       const CUtensorMap& b1, int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
+  switch (kind) {
+    case FACT_EPI_SPLIT:
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_SPLIT>(a0, a1, b0, b1, m, n, k, ep, st);
+    case FACT_EPI_BIAS_GELU_SPLIT:
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_GELU_SPLIT>(a0, a1, b0, b1, m, n, k, ep, st);
+    case FACT_EPI_BIAS_RESID_F32:
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_RESID_F32>(a0, a1, b0, b1, m, n, k, ep, st);
+    case FACT_EPI_BIAS_F32:
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_F32>(a0, a1, b0, b1, m, n, k, ep, st);
+  }
+  set_error("unknown epilogue kind %d", kind);
+  return FACT_ERR_UNSUPPORTED;
+}
+
 template <int BN, int NPART, int STAGES>
 static int launch_epi(int kind, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
                       const CUtensorMap& b1, int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
@@ -414,6 +632,8 @@ int gemm_tile_n(int n) {
   if (n % 256 == 0) return 256;  // 3072 = 12 x 256
   return 128;
 }
+
+int g_gemm_pair = 1;  // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -458,18 +678,32 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
 
   const int bn = gemm_tile_n(n);
   const bool precise = a_lo != nullptr;
+  // CTA-pair kernel (256 x BN tiles) once there is at least one pair tile per cluster; the 1-SM kernel keeps the
+  // small problems (batch-1 decode) on more SMs
+  const bool pair = g_gemm_pair && bn != 128 &&
+                    (g_gemm_pair == 2 ||  // 2 = forced (tests)
+                     static_cast<long long>((m + 2 * BM - 1) / (2 * BM)) * ((n + bn - 1) / bn) >= num_sms() / 2);
+  const int b_box = pair ? bn / 2 : bn;
   CUtensorMap a0, a1, b0, b1;
   int rc;
   if ((rc = make_tmap_bf16(&a0, a_hi, m, k, lda, BM, BK))) return rc;
-  if ((rc = make_tmap_bf16(&b0, w_hi, n, k, ldw, bn, BK))) return rc;
+  if ((rc = make_tmap_bf16(&b0, w_hi, n, k, ldw, b_box, BK))) return rc;
   if (precise) {
     if ((rc = make_tmap_bf16(&a1, a_lo, m, k, lda, BM, BK))) return rc;
-    if ((rc = make_tmap_bf16(&b1, w_lo, n, k, ldw, bn, BK))) return rc;
+    if ((rc = make_tmap_bf16(&b1, w_lo, n, k, ldw, b_box, BK))) return rc;
   } else {
     a1 = a0;
     b1 = b0;
   }
   cudaStream_t st = as_stream(stream);
+  if (pair) {
+    if (precise) {
+      if (bn == 160) return launch_epi2<160, 2, 4>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+      return launch_epi2<256, 2, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+    }
+    if (bn == 160) return launch_epi2<160, 1, 8>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+    return launch_epi2<256, 1, 6>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+  }
   if (precise) {
     if (bn == 160) return launch_epi<160, 2, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
     if (bn == 256) return launch_epi<256, 2, 2>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);

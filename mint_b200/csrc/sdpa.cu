@@ -264,6 +264,7 @@ static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int b
 
 int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
                 cudaStream_t st);
+extern int g_gemm_pair;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
 
 }  // namespace fact
@@ -273,6 +274,10 @@ using namespace fact;
 extern "C" int fact_set_flag(const char* name, int value) {
   if (name && strcmp(name, "sdpa_legacy") == 0) {
     g_sdpa_legacy = value;
+    return FACT_OK;
+  }
+  if (name && strcmp(name, "gemm_pair") == 0) {
+    g_gemm_pair = value;
     return FACT_OK;
   }
   set_error("fact_set_flag: unknown flag %s", name ? name : "(null)");

@@ -123,6 +123,40 @@ def test_gemm_tc(fact_lib, cuda, m, n, k, kind, precise):
     _gemm_case(fact_lib, cuda, m, n, k, kind, precise)
 
 
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32])
+@pytest.mark.parametrize("m,n,k", [(256, 160, 64), (360, 2400, 800), (300, 800, 3072), (700, 3072, 800),
+                                   (1000, 320, 136)])
+def test_gemm_tc_pair_forced(fact_lib, cuda, m, n, k, kind, precise):
+    """cta_group::2 kernel forced on small problems: partial pair tiles (rows of the second CTA out of range)."""
+    fact_lib.fact_set_flag(b"gemm_pair", 2)
+    try:
+        _gemm_case(fact_lib, cuda, m, n, k, kind, precise, seed=7)
+    finally:
+        fact_lib.fact_set_flag(b"gemm_pair", 1)
+
+
+def test_gemm_pair_vs_single_bitwise(fact_lib, cuda):
+    """Same operands through the 1-SM and the CTA-pair kernels: identical accumulation order -> identical bits."""
+    m, n, k = 5000, 2400, 800
+    a = torch.randn(m, k, device=cuda)
+    w = torch.randn(k, n, device=cuda) / math.sqrt(k)
+    a_hi, a_lo = split_ref(a)
+    w_hi, w_lo = split_ref(w.t().contiguous())
+    outs = []
+    for flag in (0, 2):
+        fact_lib.fact_set_flag(b"gemm_pair", flag)
+        o_hi = torch.zeros(m, n, dtype=torch.bfloat16, device=cuda)
+        o_lo = torch.zeros_like(o_hi)
+        e = _epi(kind=L.EPI_SPLIT, out_hi=o_hi, out_lo=o_lo, ldo=n, scale=1.0, scale_cols=0)
+        L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr(), k, w_hi.data_ptr(), w_lo.data_ptr(), k, m, n, k,
+                                   C.byref(e), _st()))
+        torch.cuda.synchronize()
+        outs.append((o_hi.clone(), o_lo.clone()))
+    fact_lib.fact_set_flag(b"gemm_pair", 1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_gemm_tc_remap(fact_lib, cuda):
     _gemm_case(fact_lib, cuda, 3 * 120, 800, 3072, L.EPI_BIAS_RESID_F32, True, remap=(120, 360, 0))
     _gemm_case(fact_lib, cuda, 3 * 240, 800, 3072, L.EPI_BIAS_RESID_F32, False, remap=(240, 360, 120))
