@@ -153,7 +153,9 @@ FACT_API int fact_gemm_f32(const float* a, int lda, const float* w_keras, int m,
 FACT_API int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
               int head_dim, void* stream);
 
-/* Developer switches. "sdpa_legacy" = 1 forces the generic mma.sync attention kernel instead of the tcgen05 one. */
+/* Developer switches (defaults in brackets): "sdpa_legacy" [0] = 1 forces the generic mma.sync attention kernel;
+ * "gemm_pair" [1] = 0 forces the 1-SM GEMM, 2 forces the CTA-pair GEMM; "ar_prune" [1] = 0 runs the full last layer
+ * in fact_infer_auto_regressive instead of the row-0 tail. */
 FACT_API int fact_set_flag(const char* name, int value);
 
 /* LinearEmbedding + PositionEmbedding (fact_model.py:88-90,94-95; base_models.py:135,156):

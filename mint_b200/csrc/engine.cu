@@ -20,10 +20,12 @@ namespace fact {
 int gemm_simt_split(const void* a_hi, const void* a_lo, int lda, const float* w_keras, int m, int n, int k,
                     const fact_gemm_epilogue* epi, cudaStream_t st);
 int step_set(int* p, int v, cudaStream_t st);
+int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
+             int head_dim, int q_rows, cudaStream_t st);
 int step_inc(int* p, cudaStream_t st);
 
 struct Workspace {
-  float *xm, *xa, *xc;
+  float *xm, *xa, *xc, *xr;
   bf16 *ln_hi, *ln_lo, *ao_hi, *ao_lo, *qkv_hi, *qkv_lo, *h_hi, *h_lo;
 };
 
@@ -44,6 +46,7 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
   w.xm = reinterpret_cast<float*>(take(tm * d * 4));
   w.xa = reinterpret_cast<float*>(take(ta * d * 4));
   w.xc = reinterpret_cast<float*>(take(tc * d * 4));
+  w.xr = reinterpret_cast<float*>(take(static_cast<size_t>(batch) * d * 4));  // row 0 of every clip (AR tail)
   w.ln_hi = reinterpret_cast<bf16*>(take(tc * d * 2));
   w.ln_lo = lo ? reinterpret_cast<bf16*>(take(tc * d * 2)) : nullptr;
   w.ao_hi = reinterpret_cast<bf16*>(take(tc * d * 2));
@@ -130,6 +133,56 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
   return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, M, d, ff, &e, st);
 }
 
+// Last cross-modal layer of an AR step: infer_auto_regressive keeps only output row 0 of each clip
+// (fact_model.py:128), and rows do not mix after the attention core, so everything downstream of it runs on
+// `batch` rows instead of batch*seq: the attention core computes query block 0 only, out-proj / LN / FFN read row 0 of
+// each clip through a row pitch of seq*d and write the compact buffer ws.xr [batch, d].  Results for row 0 are
+// bit-identical to the full layer.
+static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, float* x, int batch, int seq, int mode,
+                          const Workspace& ws, cudaStream_t st) {
+  const int d = dm->d_model, ff = dm->d_ff, H = dm->n_heads, dh = d / H;
+  const int M = batch * seq;
+  const bool lo = mode != FACT_MODE_BF16;
+  int rc;
+  if ((rc = fact_layernorm_split(x, L.ln1_gamma, L.ln1_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
+  fact_gemm_epilogue e{};
+  e.kind = FACT_EPI_SPLIT;
+  e.out_hi = ws.qkv_hi;
+  e.out_lo = lo ? ws.qkv_lo : nullptr;
+  e.ldo = 3 * d;
+  e.scale = static_cast<float>(1.0 / sqrt(static_cast<double>(d)) * 1.4426950408889634);
+  e.scale_cols = d;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st))) return rc;
+  if ((rc = sdpa_run(ws.qkv_hi, lo ? ws.qkv_lo : nullptr, ws.ao_hi, lo ? ws.ao_lo : nullptr, batch, seq, H, dh, 1, st)))
+    return rc;
+  const int pitch = seq * d;  // row 0 of clip b lives at b * seq * d
+  e = fact_gemm_epilogue{};
+  e.kind = FACT_EPI_BIAS_RESID_F32;
+  e.out_f32 = ws.xr;
+  e.ldo = d;
+  e.bias = L.bo;
+  e.resid = x;
+  e.ldr = pitch;
+  if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, pitch, L.wo_hi, L.wo_lo, L.wo_f32, batch, d, d, &e, st))) return rc;
+  if ((rc = fact_layernorm_split(ws.xr, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, batch, d, st)))
+    return rc;
+  e = fact_gemm_epilogue{};
+  e.kind = FACT_EPI_BIAS_GELU_SPLIT;
+  e.out_hi = ws.h_hi;
+  e.out_lo = lo ? ws.h_lo : nullptr;
+  e.ldo = ff;
+  e.bias = L.b1;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.w1_hi, L.w1_lo, L.w1_f32, batch, ff, d, &e, st))) return rc;
+  e = fact_gemm_epilogue{};
+  e.kind = FACT_EPI_BIAS_RESID_F32;
+  e.out_f32 = ws.xr;
+  e.ldo = d;
+  e.bias = L.b2;
+  e.resid = ws.xr;
+  e.ldr = d;
+  return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, batch, d, ff, &e, st);
+}
+
 static int run_stack(const fact_dims* dm, const fact_layer_weights* layers, int n_layers, float* x, int batch,
                      int seq, int mode, const Workspace& ws, float* dst, int dst_seq, int dst_off, cudaStream_t st) {
   for (int i = 0; i < n_layers; ++i) {
@@ -143,7 +196,7 @@ static int run_stack(const fact_dims* dm, const fact_layer_weights* layers, int 
 // embeddings + modality encoders + 12-layer cross-modal stack; leaves the result in ws.xc
 static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* motion, long long motion_bs,
                      const float* audio, long long audio_bs, const int* step_ptr, int batch, int mode,
-                     const Workspace& ws, cudaStream_t st) {
+                     const Workspace& ws, bool row0_only, cudaStream_t st) {
   const int d = dm->d_model, ns = dm->motion_seq + dm->audio_seq;
   int rc;
   FACT_REQUIRE(dm->motion_layers > 0 && dm->audio_layers > 0 && dm->cross_layers > 0, FACT_ERR_UNSUPPORTED,
@@ -160,7 +213,11 @@ static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* mo
   if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, ws, ws.xc, ns,
                       dm->motion_seq, st)))
     return rc;
-  return run_stack(dm, w->cross_layers, dm->cross_layers, ws.xc, batch, ns, mode, ws, nullptr, 0, 0, st);
+  if (!row0_only)
+    return run_stack(dm, w->cross_layers, dm->cross_layers, ws.xc, batch, ns, mode, ws, nullptr, 0, 0, st);
+  if ((rc = run_stack(dm, w->cross_layers, dm->cross_layers - 1, ws.xc, batch, ns, mode, ws, nullptr, 0, 0, st)))
+    return rc;
+  return run_layer_row0(dm, w->cross_layers[dm->cross_layers - 1], ws.xc, batch, ns, mode, ws, st);
 }
 
 static int check_weights(const fact_dims* dm, const fact_weights* w) {
@@ -173,6 +230,8 @@ static int check_weights(const fact_dims* dm, const fact_weights* w) {
 }
 
 // ---- graph cache for the AR loop
+int g_ar_prune = 1;  // fact_set_flag("ar_prune", 0): run the full last layer (A-B check of the row-0 pruning)
+
 struct GraphKey {
   std::vector<uintptr_t> v;
   bool operator<(const GraphKey& o) const { return v < o.v; }
@@ -205,7 +264,7 @@ extern "C" int fact_forward(const fact_dims* dims, const fact_weights* w, const 
   cudaStream_t st = as_stream(stream);
   const long long mbs = static_cast<long long>(dims->motion_seq) * dims->motion_dim;
   const long long abs_ = static_cast<long long>(dims->audio_seq) * dims->audio_dim;
-  if ((rc = run_trunk(dims, w, motion, mbs, audio, abs_, nullptr, batch, mode, ws, st))) return rc;
+  if ((rc = run_trunk(dims, w, motion, mbs, audio, abs_, nullptr, batch, mode, ws, false, st))) return rc;
   // output Dense on all 360 rows (base_models.py:200)
   const int d = dims->d_model, ns = dims->motion_seq + dims->audio_seq, M = batch * ns;
   const bool lo = mode != FACT_MODE_BF16;
@@ -252,9 +311,11 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
 
   auto one_frame = [&](cudaStream_t s) -> int {
     int r;
-    if ((r = run_trunk(dims, w, motion_hist, hist_bs, audio, audio_bs, step_counter, batch, mode, ws, s))) return r;
+    if ((r = run_trunk(dims, w, motion_hist, hist_bs, audio, audio_bs, step_counter, batch, mode, ws, g_ar_prune != 0,
+                       s)))
+      return r;
     // keep row 0 of each sample (fact_model.py:128), append it to the history at row motion_seq + step
-    if ((r = fact_head_rows(ws.xc, ns, w->out_w, w->out_b,
+    if ((r = fact_head_rows(g_ar_prune ? ws.xr : ws.xc, g_ar_prune ? 1 : ns, w->out_w, w->out_b,
                             motion_hist + static_cast<size_t>(dims->motion_seq) * dims->motion_dim, hist_bs,
                             step_counter, batch, dims->d_model, dims->out_dim, s)))
       return r;
@@ -274,7 +335,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
            reinterpret_cast<uintptr_t>(motion_hist), reinterpret_cast<uintptr_t>(audio),
            reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
            static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(hist_capacity),
-           static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers),
+           static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers + 1000 * g_ar_prune),
            static_cast<uintptr_t>(dims->d_model)};
   cudaGraphExec_t exec = nullptr;
   {

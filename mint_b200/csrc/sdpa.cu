@@ -247,7 +247,7 @@ sdpa_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, bf
 }
 
 template <int DH, int NPART>
-static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads,
+static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int q_rows,
                        cudaStream_t st) {
   constexpr int smem = 2 * (2 * NPART * SDPA_KB * (DH + 8)) * 2;
   auto kern = sdpa_kernel<DH, NPART>;
@@ -256,15 +256,16 @@ static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int b
     FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  dim3 grid((n + SDPA_QB - 1) / SDPA_QB, heads, batch);
+  dim3 grid((q_rows + SDPA_QB - 1) / SDPA_QB, heads, batch);
   kern<<<grid, SDPA_THREADS, smem, st>>>(qh, ql, oh, ol, n, heads);
   FACT_LAUNCH_CHECK("sdpa_kernel launch");
   return FACT_OK;
 }
 
 int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
-                cudaStream_t st);
+                int q_rows, cudaStream_t st);
 extern int g_gemm_pair;
+extern int g_ar_prune;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
 
 }  // namespace fact
@@ -276,6 +277,10 @@ extern "C" int fact_set_flag(const char* name, int value) {
     g_sdpa_legacy = value;
     return FACT_OK;
   }
+  if (name && strcmp(name, "ar_prune") == 0) {
+    g_ar_prune = value;
+    return FACT_OK;
+  }
   if (name && strcmp(name, "gemm_pair") == 0) {
     g_gemm_pair = value;
     return FACT_OK;
@@ -284,27 +289,29 @@ extern "C" int fact_set_flag(const char* name, int value) {
   return FACT_ERR_UNSUPPORTED;
 }
 
-extern "C" int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n,
-                         int heads, int head_dim, void* stream) {
+namespace fact {
+
+// q_rows < n: only the first q_rows query rows of every (batch, head) are needed (whole 128-row blocks are computed)
+int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
+             int head_dim, int q_rows, cudaStream_t st) {
   FACT_REQUIRE(qkv_hi && out_hi, FACT_ERR_BAD_SHAPE, "fact_sdpa: null buffer");
   FACT_REQUIRE((qkv_lo == nullptr) == (out_lo == nullptr), FACT_ERR_BAD_SHAPE,
                "fact_sdpa: qkv_lo and out_lo must both be given (precise) or both NULL (bf16)");
-  FACT_REQUIRE(batch > 0 && batch <= 65535 && n > 0 && heads > 0 && heads <= 65535, FACT_ERR_BAD_SHAPE,
-               "fact_sdpa: bad shape batch=%d n=%d heads=%d", batch, n, heads);
+  FACT_REQUIRE(batch > 0 && batch <= 65535 && n > 0 && heads > 0 && heads <= 65535 && q_rows > 0 && q_rows <= n,
+               FACT_ERR_BAD_SHAPE, "fact_sdpa: bad shape batch=%d n=%d heads=%d q_rows=%d", batch, n, heads, q_rows);
   const bf16* qh = static_cast<const bf16*>(qkv_hi);
   const bf16* ql = static_cast<const bf16*>(qkv_lo);
   bf16* oh = static_cast<bf16*>(out_hi);
   bf16* ol = static_cast<bf16*>(out_lo);
-  cudaStream_t st = as_stream(stream);
   const bool precise = qkv_lo != nullptr;
   if (!g_sdpa_legacy) {  // B200-native path: tcgen05 + TMEM-resident scores (head_dim 80, n <= 384)
-    const int rc = sdpa_tc_try(qh, ql, oh, ol, batch, n, heads, head_dim, st);
+    const int rc = sdpa_tc_try(qh, ql, oh, ol, batch, n, heads, head_dim, q_rows, st);
     if (rc != FACT_ERR_UNSUPPORTED) return rc;
   }
 #define FACT_SDPA_CASE(DHV)                                                            \
   case DHV:                                                                            \
-    return precise ? launch_sdpa<DHV, 2>(qh, ql, oh, ol, batch, n, heads, st)          \
-                   : launch_sdpa<DHV, 1>(qh, ql, oh, ol, batch, n, heads, st);
+    return precise ? launch_sdpa<DHV, 2>(qh, ql, oh, ol, batch, n, heads, q_rows, st)  \
+                   : launch_sdpa<DHV, 1>(qh, ql, oh, ol, batch, n, heads, q_rows, st);
   switch (head_dim) {
     FACT_SDPA_CASE(16)
     FACT_SDPA_CASE(32)
@@ -314,4 +321,11 @@ extern "C" int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, v
 #undef FACT_SDPA_CASE
   set_error("fact_sdpa: head_dim %d not instantiated (16, 32, 64, 80)", head_dim);
   return FACT_ERR_UNSUPPORTED;
+}
+
+}  // namespace fact
+
+extern "C" int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n,
+                         int heads, int head_dim, void* stream) {
+  return fact::sdpa_run(qkv_hi, qkv_lo, out_hi, out_lo, batch, n, heads, head_dim, n, fact::as_stream(stream));
 }

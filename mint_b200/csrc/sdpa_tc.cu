@@ -275,7 +275,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
 template <int NPART>
 static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads,
-                          cudaStream_t st) {
+                          int q_rows, cudaStream_t st) {
   using Cfg = SdpaTcCfg<NPART>;
   auto kern = sdpa_tc_kernel<NPART>;
   static bool attr_done = false;
@@ -292,7 +292,7 @@ static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, in
   } else {
     tml = tmh;
   }
-  const int q_blocks = (n + TC_QB - 1) / TC_QB;
+  const int q_blocks = (q_rows + TC_QB - 1) / TC_QB;
   const int num_tiles = q_blocks * heads * batch;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmh, tml, oh, ol, n, heads, q_blocks, num_tiles);
@@ -303,13 +303,13 @@ static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, in
 // tcgen05 path: head_dim 80, n <= 384, 16-byte aligned buffers.  Returns FACT_ERR_UNSUPPORTED (without setting an
 // error) when the shape is outside that envelope so that fact_sdpa falls back to the generic mma.sync kernel.
 int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
-                cudaStream_t st) {
+                int q_rows, cudaStream_t st) {
   if (head_dim != TC_DH || n > TC_MAXBLK * TC_KB) return FACT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(qh) | reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ql) |
        reinterpret_cast<uintptr_t>(ol)) & 15)
     return FACT_ERR_UNSUPPORTED;
-  return ql ? launch_sdpa_tc<2>(qh, ql, oh, ol, batch, n, heads, st)
-            : launch_sdpa_tc<1>(qh, ql, oh, ol, batch, n, heads, st);
+  return ql ? launch_sdpa_tc<2>(qh, ql, oh, ol, batch, n, heads, q_rows, st)
+            : launch_sdpa_tc<1>(qh, ql, oh, ol, batch, n, heads, q_rows, st);
 }
 
 }  // namespace fact

@@ -128,6 +128,21 @@ def test_ar_parity_v5(cuda, fact_lib):
     assert (single - out[:, 1]).abs().max() < 1e-4
 
 
+def test_ar_row0_pruning_is_exact(cuda, fact_lib):
+    """The pruned last layer (row 0 only) must reproduce the full last layer bit for bit on the kept row."""
+    dims = oracle_dims()
+    w = O.init_weights(dims, seed=2)
+    inp = O.synthetic_inputs(dims, batch=3, audio_len=dims.audio_seq + 2, seed=2)
+    tin = {k: torch.from_numpy(v).float() for k, v in inp.items()}
+    outs = []
+    for flag in (1, 0):
+        fact_lib.fact_set_flag(b"ar_prune", flag)
+        m = _model(make_config(), w, "precise")
+        outs.append(m.infer_auto_regressive(tin, steps=3).cpu())
+    fact_lib.fact_set_flag(b"ar_prune", 1)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_model_builder_and_config(cuda, fact_lib):
     cfg = config_util.get_configs_from_pipeline_file(config_util.DEFAULT_CONFIG)
     m = model_builder.build(cfg["model"], True)
