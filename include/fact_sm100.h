@@ -120,6 +120,8 @@ FACT_API int fact_layernorm_split(const float* x, const float* gamma, const floa
 #define FACT_EPI_BIAS_GELU_SPLIT 1 /* out_hi/lo = split(gelu_tanh(acc + bias))   (base_model_util.py:94) */
 #define FACT_EPI_BIAS_RESID_F32 2  /* out_f32[map(row)] = acc + bias + resid[row]                        */
 #define FACT_EPI_BIAS_F32 3        /* out_f32 = acc + bias                                               */
+#define FACT_EPI_BIAS_GELU_SAVE 4  /* z = acc + bias: out_hi = bf16(gelu_tanh(z)), out_lo = bf16(z) (training fwd)  */
+#define FACT_EPI_GELU_GRAD 5       /* out_hi = bf16(acc * gelu_tanh'(aux[row, col]))  (aux = saved z, bf16)          */
 
 typedef struct fact_gemm_epilogue {
   int kind;           /* FACT_EPI_* */
@@ -135,6 +137,8 @@ typedef struct fact_gemm_epilogue {
   /* output-row remap for zero-copy concat (base_models.py:192-193): out_row = (row / seq_in) * seq_out + seq_off
    * + row % seq_in ; seq_in == 0 disables it */
   int seq_in, seq_out, seq_off;
+  const void* aux;    /* FACT_EPI_GELU_GRAD: bf16 [m, ldaux] pre-activation saved by FACT_EPI_BIAS_GELU_SAVE */
+  int ldaux;
 } fact_gemm_epilogue;
 
 /* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).
@@ -194,6 +198,48 @@ FACT_API int fact_infer_auto_regressive(const fact_dims* dims, const fact_weight
                                         int hist_capacity, const float* audio, int audio_len, int batch,
                                         int start_frame, int n_frames, int* step_counter, void* workspace,
                                         size_t workspace_bytes, int mode, int use_graph, void* stream);
+
+/* ---- training blocks (bf16 product path; reference semantics: mint/ctl/single_task_trainer.py:138-199) -------- */
+
+/* Attention core with the per-row log2-sum-exp saved for the backward pass: lse[(b*heads + h)*n + row] (may be NULL).
+ * Same contract as fact_sdpa otherwise. */
+FACT_API int fact_sdpa_lse(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, float* lse, int batch,
+                           int n, int heads, int head_dim, void* stream);
+
+/* dW[in_dim, out_dim] += X^T . dY  (Keras-layout gradient of a Dense kernel): x_bf16 [tokens, ldx], dy_bf16 [tokens,
+ * ldy], fp32 accumulate with atomics (zero dw first).  tcgen05, both operands MN-major through TMA, split-K. */
+FACT_API int fact_wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dw, int ldw, int tokens,
+                             int in_dim, int out_dim, void* stream);
+
+/* Backward of fact_sdpa: qkv bf16 [batch*n, 3d] as written by the forward QKV epilogue (q pre-scaled), o / d_o bf16
+ * [batch*n, d], lse from fact_sdpa_lse; writes dqkv bf16 [batch*n, 3d] = d loss / d (unscaled q, k, v).
+ * d_scratch: fp32 [batch*heads*n]; dq_scratch: fp32 [batch*n*d]; scale = d_model^-0.5. */
+FACT_API int fact_sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* d_scratch,
+                                float* dq_scratch, void* dqkv, int batch, int n, int heads, int head_dim, float scale,
+                                void* stream);
+
+/* dx = dres + d LayerNorm(x; gamma)^T dy (dres may be NULL); dgamma / dbeta accumulate (zero them first). */
+FACT_API int fact_layernorm_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx,
+                                     float* dgamma, float* dbeta, int rows, int d, void* stream);
+
+/* Gradients of fact_embed: dw[f, d] += x^T dy, dbias[d] += colsum(dy), dpos[n_tok, d] += sum over clips (may be NULL). */
+FACT_API int fact_embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dw, float* dbias,
+                                 float* dpos, int batch, int n_tok, int f, int d, void* stream);
+
+/* y_bf16[r, 0:ldy] = bf16(x[r, 0:n]) zero padded, colsum[c] += sum_r x[r, c] (either output may be NULL). */
+FACT_API int fact_cast_colsum(const float* x, int ldx, void* y_bf16, int ldy, float* colsum, int rows, int n,
+                              void* stream);
+
+/* bf16 copy of a Keras-layout kernel [rows, cols] with row pitch ld_out (zero padded): B operand of dX = dY . W^T. */
+FACT_API int fact_cast_weight(const float* w_keras, void* out_bf16, int rows, int cols, int ld_out, void* stream);
+
+/* Keras Adam (trainer.py:150; beta1 .9, beta2 .999, epsilon 1e-7 outside the root) on a flat range;
+ * g is multiplied by grad_scale first (global-norm clipping). step counts from 1. */
+FACT_API int fact_adam_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                            float beta2, float eps, long long step, float grad_scale, void* stream);
+
+/* *out = sum g^2 (for clip_by_global_norm, single_task_trainer.py:180-183). */
+FACT_API int fact_sum_squares(const float* g, long long n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,763 @@
+// Backward kernels of the FACT training step (reference semantics: mint/ctl/single_task_trainer.py:138-199 --
+// tape.gradient of FACTModel.loss through FACTModel.call; Keras Adam at trainer.py:150).  Training runs the bf16
+// product path (BASELINE.json configs[2] "training step bf16"): bf16 operands, fp32 accumulation, fp32 master weights.
+//
+//   gemm_wgrad_kernel   dW[in,out] += X^T . dY   tcgen05, BOTH operands MN-major through TMA (no transposes in HBM),
+//                       split-K over tokens, fp32 red.add epilogue straight into the Keras-layout gradient
+//   (dX = dY . W^T reuses gemm_tc_kernel with the Keras-layout bf16 weight as the K-major B operand)
+//   sdpa_bwd_*          attention-core backward, flash style (mma.sync), recomputing P from the saved log-sum-exp
+//   ln_bwd_kernel       LayerNorm backward + residual-gradient add, per-block partial dgamma / dbeta
+//   cast_colsum_kernel  fp32 -> bf16 operand cast fused with the bias gradient (column sums)
+//   embed_bwd_kernel    LinearEmbedding / PositionEmbedding gradients
+//   adam_kernel         Keras Adam (epsilon OUTSIDE the square root, bias correction folded into the step size)
+#include "fact_internal.h"
+#include "fact_ptx.cuh"
+
+namespace fact {
+
+// =========================================================================================== weight-gradient GEMM
+constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 6, WG_THREADS = 192;
+constexpr int WG_BOX_BYTES = 64 * 64 * 2;                 // one {64 MN, 64 K} box
+constexpr int WG_STAGE_BYTES = 4 * WG_BOX_BYTES;          // A: 2 boxes, B: 2 boxes
+constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
+
+// C[in, out] (+)= sum_t X[t, in] * dY[t, out].  tmX: tensor {in (inner), tokens}, tmY: tensor {out (inner), tokens}.
+// grid = (tiles_out, tiles_in, splits); CTA handles K blocks [z * kb_per, min((z+1) * kb_per, num_kb)).
+__global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(
+    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, float* __restrict__ dW, int ldw,
+    int IN, int OUT, int num_kb, int kb_per) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * WG_STAGES);
+  const uint32_t tmem_ptr_addr = done_bar + 8;
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + WG_STAGES * WG_STAGE_BYTES + 8 * (2 * WG_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * WG_BN, m0 = blockIdx.y * WG_BM;
+  const int kb0 = blockIdx.z * kb_per;
+  const int kb1 = min(kb0 + kb_per, num_kb);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_ptr_addr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  auto sA = [&](int s) { return smem_base + s * WG_STAGE_BYTES; };
+  auto sB = [&](int s) { return smem_base + s * WG_STAGE_BYTES + 2 * WG_BOX_BYTES; };
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % WG_STAGES;
+          mbar_wait(empty_bar(s), ((i / WG_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), WG_STAGE_BYTES);
+          const int t0 = (kb0 + i) * WG_BK;
+          tma_load_2d(sA(s), &tmX, m0, t0, full_bar(s));
+          tma_load_2d(sA(s) + WG_BOX_BYTES, &tmX, m0 + 64, t0, full_bar(s));
+          tma_load_2d(sB(s), &tmY, n0, t0, full_bar(s));
+          tma_load_2d(sB(s) + WG_BOX_BYTES, &tmY, n0 + 64, t0, full_bar(s));
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16_f32_maj(WG_BM, WG_BN, 1, 1);
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % WG_STAGES;
+          mbar_wait(full_bar(s), (i / WG_STAGES) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < WG_BK / 16; ++kk) {  // 16 tokens = two 8-row groups = 2048 bytes
+            const uint64_t a = umma_desc_mn_sw128(sA(s) + kk * 2048, WG_BOX_BYTES, 1024);
+            const uint64_t b = umma_desc_mn_sw128(sB(s) + kk * 2048, WG_BOX_BYTES, 1024);
+            umma_bf16(tmem_base, a, b, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(done_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < WG_BN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (row < IN) {
+          float* dst = dW + static_cast<size_t>(row) * ldw + n0 + c0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (n0 + c0 + c < OUT) atomicAdd(dst + c, v[c]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// =========================================================================================== attention backward
+// D[b,h,row] = sum_d dO * O  (softmax-backward row term), one warp per (token, head)
+__global__ void __launch_bounds__(256) sdpa_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                            float* __restrict__ Dv, int tokens, int N, int H, int DH) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= tokens * H) return;
+  const int tok = gw / H, h = gw % H;
+  const bf16* po = o + static_cast<size_t>(tok) * H * DH + h * DH;
+  const bf16* pd = d_o + static_cast<size_t>(tok) * H * DH + h * DH;
+  float s = 0.f;
+  for (int i = lane; i < DH; i += 32) s += __bfloat162float(po[i]) * __bfloat162float(pd[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    const int b = tok / N, r = tok % N;
+    Dv[(static_cast<size_t>(b) * H + h) * N + r] = s;
+  }
+}
+
+// One CTA per (batch, head, 64-key block); 4 warps x 16 keys.  For every 64-query block: recompute P^T from the saved
+// log2-sum-exp, accumulate dV, dK in registers; dQ contributions go through a shared transposed tile and fp32 atomics.
+// qkv holds q' = q * scale * log2(e) (as written by the QKV epilogue), k, v.  Outputs: dqkv[:, d:2d] = dK, [:, 2d:3d] = dV
+// (bf16), dq_acc (fp32, += dZ . K, unscaled).
+template <int DH>
+__global__ void __launch_bounds__(128, 1) sdpa_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                          const float* __restrict__ lse, const float* __restrict__ Dv,
+                                                          bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int N,
+                                                          int H, float k_scale) {
+  constexpr int DHP = DH + 8, KS = DH / 16, DT = DH / 8, CH = DH / 8, BLK = 64, ZP = BLK + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Ks = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Vs = Ks + BLK * DHP;
+  bf16* Qs = Vs + BLK * DHP;          // 2 stages
+  bf16* Os = Qs + 2 * BLK * DHP;      // dO, 2 stages
+  bf16* Zs = Os + 2 * BLK * DHP;      // dZ^T [key][query]
+  float* Ls = reinterpret_cast<float*>(Zs + BLK * ZP);  // lse, 2 stages
+  float* Ds = Ls + 2 * BLK;                              // D, 2 stages
+
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int D = H * DH, LD = 3 * D;
+  const size_t tok0 = static_cast<size_t>(b) * N;
+  const int j0 = jb * BLK;
+
+  for (int c = threadIdx.x; c < 2 * BLK * CH; c += 128) {
+    const int which = c / (BLK * CH), rem = c % (BLK * CH), r = rem / CH, cc = rem % CH;
+    const bool ok = j0 + r < N;
+    const bf16* src = qkv + (tok0 + (ok ? j0 + r : 0)) * LD + (1 + which) * D + h * DH + cc * 8;
+    cp_async16(smem_u32((which ? Vs : Ks) + r * DHP + cc * 8), src, ok);
+  }
+  auto load_q = [&](int ib, int st) {
+    const int i0 = ib * BLK;
+    for (int c = threadIdx.x; c < 2 * BLK * CH; c += 128) {
+      const int which = c / (BLK * CH), rem = c % (BLK * CH), r = rem / CH, cc = rem % CH;
+      const bool ok = i0 + r < N;
+      const size_t tok = tok0 + (ok ? i0 + r : 0);
+      const bf16* src = which ? d_o + tok * D + h * DH + cc * 8 : qkv + tok * LD + h * DH + cc * 8;
+      cp_async16(smem_u32((which ? Os : Qs) + st * BLK * DHP + r * DHP + cc * 8), src, ok);
+    }
+    if (threadIdx.x < BLK) {
+      const int r = i0 + threadIdx.x;
+      const size_t idx = (static_cast<size_t>(b) * H + h) * N + (r < N ? r : 0);
+      Ls[st * BLK + threadIdx.x] = r < N ? lse[idx] : 0.f;
+      Ds[st * BLK + threadIdx.x] = r < N ? Dv[idx] : 0.f;
+    }
+  };
+  load_q(0, 0);
+  cp_async_commit();
+
+  float dk[DT][4], dv[DT][4];
+#pragma unroll
+  for (int i = 0; i < DT; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
+
+  const int nqb = (N + BLK - 1) / BLK;
+  const int mat = lane >> 3, r8 = lane & 7;
+  for (int ib = 0; ib < nqb; ++ib) {
+    const int st = ib & 1;
+    if (ib + 1 < nqb) load_q(ib + 1, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const bf16* Q = Qs + st * BLK * DHP;
+    const bf16* dO = Os + st * BLK * DHP;
+    const float* L = Ls + st * BLK;
+    const float* Dd = Ds + st * BLK;
+    const int i0 = ib * BLK;
+
+    // (1) S^T = K_w . Q^T   and (4) dP^T = V_w . dO^T      [16 keys x 64 queries each]
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[i][e] = dp[i][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t ak[4], av[4];
+      const int arow = warp * 16 + (mat & 1) * 8 + r8, acol = ks * 16 + (mat >> 1) * 8;
+      ldsm_x4(smem_u32(Ks + arow * DHP + acol), ak[0], ak[1], ak[2], ak[3]);
+      ldsm_x4(smem_u32(Vs + arow * DHP + acol), av[0], av[1], av[2], av[3]);
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp) {
+        const int brow = ntp * 16 + (mat >> 1) * 8 + r8, bcol = ks * 16 + (mat & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(Q + brow * DHP + bcol), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * ntp], ak, b0, b1);
+        mma_bf16_16816(s[2 * ntp + 1], ak, b2, b3);
+        ldsm_x4(smem_u32(dO + brow * DHP + bcol), b0, b1, b2, b3);
+        mma_bf16_16816(dp[2 * ntp], av, b0, b1);
+        mma_bf16_16816(dp[2 * ntp + 1], av, b2, b3);
+      }
+    }
+    // (2) P^T = 2^(S^T - lse[query]) ; (5) dZ^T = P^T * (dP^T - D[query]) ; masked outside [0, N)
+    uint32_t pa[4][4], za[4][4];  // A fragments (16 keys x 16 queries per k-step) of P^T and dZ^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float pz[4], zz[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = nt * 8 + 2 * t + (e & 1);
+        const int key = j0 + warp * 16 + g + (e >> 1) * 8;
+        const bool ok = (i0 + qi < N) && (key < N);
+        const float p = ok ? ex2_approx(s[nt][e] - L[qi]) : 0.f;
+        pz[e] = p;
+        zz[e] = p * (dp[nt][e] - Dd[qi]);
+      }
+      const int kk = nt >> 1, hi = nt & 1;
+      pa[kk][hi * 2 + 0] = cvt_bf16x2(pz[0], pz[1]);
+      pa[kk][hi * 2 + 1] = cvt_bf16x2(pz[2], pz[3]);
+      za[kk][hi * 2 + 0] = cvt_bf16x2(zz[0], zz[1]);
+      za[kk][hi * 2 + 1] = cvt_bf16x2(zz[2], zz[3]);
+      // transposed tile for the dQ product: Zs[key][query]
+      const int kr = warp * 16 + g, qc = nt * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(Zs + kr * ZP + qc) = za[kk][hi * 2 + 0];
+      *reinterpret_cast<uint32_t*>(Zs + (kr + 8) * ZP + qc) = za[kk][hi * 2 + 1];
+    }
+    // (3) dV_w += P^T . dO     (6) dK_w += dZ^T . Q        [B operand: rows = query, n = dh -> transposed ldmatrix]
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int vrow = kk * 16 + (mat & 1) * 8 + r8;
+#pragma unroll
+      for (int dtp = 0; dtp < DT / 2; ++dtp) {
+        const int col = (2 * dtp + (mat >> 1)) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(dO + vrow * DHP + col), b0, b1, b2, b3);
+        mma_bf16_16816(dv[2 * dtp], pa[kk], b0, b1);
+        mma_bf16_16816(dv[2 * dtp + 1], pa[kk], b2, b3);
+        ldsm_x4_t(smem_u32(Q + vrow * DHP + col), b0, b1, b2, b3);
+        mma_bf16_16816(dk[2 * dtp], za[kk], b0, b1);
+        mma_bf16_16816(dk[2 * dtp + 1], za[kk], b2, b3);
+      }
+    }
+    __syncthreads();  // Zs complete
+    // (7) dQ[16 queries of this warp x DH] = dZ[query, key] . K[key, dh]
+    {
+      float dq[DT][4];
+#pragma unroll
+      for (int i = 0; i < DT; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+        // A[m = query][k = key] read transposed from Zs[key][query]
+        uint32_t a[4];
+        {
+          const int krow = kk * 16 + (mat >> 1) * 8 + r8;       // matrices 0,1: keys 0-7 ; 2,3: keys 8-15
+          const int qcol = warp * 16 + (mat & 1) * 8;           // matrices 0,2: queries 0-7 ; 1,3: queries 8-15
+          ldsm_x4_t(smem_u32(Zs + krow * ZP + qcol), a[0], a[1], a[2], a[3]);
+        }
+        const int vrow = kk * 16 + (mat & 1) * 8 + r8;
+#pragma unroll
+        for (int dtp = 0; dtp < DT / 2; ++dtp) {
+          const int col = (2 * dtp + (mat >> 1)) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(smem_u32(Ks + vrow * DHP + col), b0, b1, b2, b3);
+          mma_bf16_16816(dq[2 * dtp], a, b0, b1);
+          mma_bf16_16816(dq[2 * dtp + 1], a, b2, b3);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int qrow = i0 + warp * 16 + g + i * 8;
+        if (qrow < N) {
+          float* dst = dq_acc + (tok0 + qrow) * D + h * DH + 2 * t;
+#pragma unroll
+          for (int dt = 0; dt < DT; ++dt) {
+            atomicAdd(dst + dt * 8, dq[dt][2 * i]);
+            atomicAdd(dst + dt * 8 + 1, dq[dt][2 * i + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // Q/dO stage and Zs are reused by the next iteration
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int key = j0 + warp * 16 + g + i * 8;
+    if (key < N) {
+      bf16* pk = dqkv + (tok0 + key) * LD + D + h * DH + 2 * t;
+      bf16* pv = pk + D;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        *reinterpret_cast<uint32_t*>(pk + dt * 8) = cvt_bf16x2(dk[dt][2 * i] * k_scale, dk[dt][2 * i + 1] * k_scale);
+        *reinterpret_cast<uint32_t*>(pv + dt * 8) = cvt_bf16x2(dv[dt][2 * i], dv[dt][2 * i + 1]);
+      }
+    }
+  }
+}
+
+// dqkv[:, 0:d] = bf16(dq_acc * scale)
+__global__ void __launch_bounds__(256) sdpa_bwd_finish_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv,
+                                                              long long tokens, int D, float scale) {
+  const long long total = tokens * (D / 4);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long tok = i / (D / 4);
+    const int c = static_cast<int>(i % (D / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(dq_acc + tok * D + c);
+    uint2 o;
+    o.x = cvt_bf16x2(v.x * scale, v.y * scale);
+    o.y = cvt_bf16x2(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(dqkv + tok * 3 * D + c) = o;
+  }
+}
+
+// =========================================================================================== LayerNorm backward
+// dx_out = dres + LN'(x; gamma)^T dy ; per-block partial dgamma / dbeta reduced with atomics.  One warp per row,
+// each block walks rows blockIdx.x, +gridDim.x ...  (d <= 1024, d % 4 == 0)
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ dy, const float* __restrict__ dres,
+                                                     float* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int rows, int d) {
+  __shared__ float sg[1024], sb[1024];
+  for (int i = threadIdx.x; i < d; i += 256) sg[i] = sb[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = d >> 2;
+  float4 ag[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
+    const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * d);
+    float4 v[8], gdy[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + i * 32;
+      v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane + i * 32 < nv) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / d + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;  // sum(g*dy), sum(g*dy*xhat)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float4 dyv = yr[idx];
+        const float4 gg = *reinterpret_cast<const float4*>(gamma + idx * 4);
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+        gdy[i] = make_float4(gg.x * dyv.x, gg.y * dyv.y, gg.z * dyv.z, gg.w * dyv.w);
+        s1 += (gdy[i].x + gdy[i].y) + (gdy[i].z + gdy[i].w);
+        s2 += (gdy[i].x * v[i].x + gdy[i].y * v[i].y) + (gdy[i].z * v[i].z + gdy[i].w * v[i].w);
+        ag[i].x += dyv.x * v[i].x; ag[i].y += dyv.y * v[i].y; ag[i].z += dyv.z * v[i].z; ag[i].w += dyv.w * v[i].w;
+        ab[i].x += dyv.x; ab[i].y += dyv.y; ab[i].z += dyv.z; ab[i].w += dyv.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / d, m2 = s2 / d;
+    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * d) : nullptr;
+    float4* outr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        float4 o4;
+        o4.x = rstd * (gdy[i].x - m1 - v[i].x * m2);
+        o4.y = rstd * (gdy[i].y - m1 - v[i].y * m2);
+        o4.z = rstd * (gdy[i].z - m1 - v[i].z * m2);
+        o4.w = rstd * (gdy[i].w - m1 - v[i].w * m2);
+        if (rr) {
+          const float4 r4 = rr[idx];
+          o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
+        }
+        outr[idx] = o4;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      atomicAdd(&sg[idx * 4 + 0], ag[i].x); atomicAdd(&sg[idx * 4 + 1], ag[i].y);
+      atomicAdd(&sg[idx * 4 + 2], ag[i].z); atomicAdd(&sg[idx * 4 + 3], ag[i].w);
+      atomicAdd(&sb[idx * 4 + 0], ab[i].x); atomicAdd(&sb[idx * 4 + 1], ab[i].y);
+      atomicAdd(&sb[idx * 4 + 2], ab[i].z); atomicAdd(&sb[idx * 4 + 3], ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += 256) {
+    atomicAdd(dgamma + i, sg[i]);
+    atomicAdd(dbeta + i, sb[i]);
+  }
+}
+
+// =========================================================================================== cast + column sums
+// y_bf16[r, c] = bf16(x[r, c]) (row pitch ldy, zero padding of columns [n, ldy)); colsum[c] += sum_r x[r, c] (optional)
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ x, int ldx, bf16* __restrict__ y,
+                                                          int ldy, float* __restrict__ colsum, int rows, int n,
+                                                          int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < ldy; c += 256) {
+    float s = 0.f;
+    if (c < n) {
+      for (int r = r0; r < r1; ++r) {
+        const float v = x[static_cast<size_t>(r) * ldx + c];
+        s += v;
+        if (y) y[static_cast<size_t>(r) * ldy + c] = __float2bfloat16_rn(v);
+      }
+      if (colsum) atomicAdd(colsum + c, s);
+    } else if (y) {
+      for (int r = r0; r < r1; ++r) y[static_cast<size_t>(r) * ldy + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+// column sums of a bf16 matrix (bias gradient of the FFN hidden layer)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int ldx,
+                                                          float* __restrict__ colsum, int rows, int n,
+                                                          int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < n; c += 256) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += __bfloat162float(x[static_cast<size_t>(r) * ldx + c]);
+    atomicAdd(colsum + c, s);
+  }
+}
+
+// gather / scatter of the per-clip row slices between [B*seq_in, d] and [B*seq_out, d] (concat backward)
+__global__ void __launch_bounds__(256) slice_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         long long rows_dst, int d, int seq_dst, int seq_src,
+                                                         int seq_off) {
+  const long long total = rows_dst * (d / 4);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long r = i / (d / 4);
+    const int c = static_cast<int>(i % (d / 4));
+    const long long sr = (r / seq_dst) * seq_src + seq_off + r % seq_dst;
+    reinterpret_cast<float4*>(dst)[r * (d / 4) + c] = reinterpret_cast<const float4*>(src)[sr * (d / 4) + c];
+  }
+}
+
+// =========================================================================================== embedding backward
+// dW[f, c] += sum_r x[r, f] * dy[r, c] ; dpos[r % n_tok, c] += dy[r, c] ; dbias[c] += sum_r dy[r, c]
+// grid (d / 64, rows / 256): each block owns 64 output columns and 256 rows; threads: 64 columns x 4 row lanes
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ x, long long x_batch_stride,
+                                                        const float* __restrict__ dy, float* __restrict__ dW,
+                                                        float* __restrict__ dbias, float* __restrict__ dpos, int rows,
+                                                        int n_tok, int f, int d) {
+  extern __shared__ float xs[];  // [64 rows][f]
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;  // 0..3
+  const int rbase = blockIdx.y * 256;
+  float bsum = 0.f;
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    const int r0 = rbase + chunk * 64;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * f; e += 256) {
+      const int r = r0 + e / f, k = e % f;
+      xs[e] = r < rows ? x[static_cast<size_t>(r / n_tok) * x_batch_stride + static_cast<size_t>(r % n_tok) * f + k] : 0.f;
+    }
+    __syncthreads();
+    // each thread: its column c, rows rl, rl+4, ... of the chunk; accumulate dW[k, c] over those rows per k
+    float dyv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = r0 + rl + 4 * i;
+      dyv[i] = (r < rows && c < d) ? dy[static_cast<size_t>(r) * d + c] : 0.f;
+      bsum += dyv[i];
+      if (r < rows && c < d && dpos) atomicAdd(dpos + static_cast<size_t>(r % n_tok) * d + c, dyv[i]);
+    }
+    if (c < d) {
+      for (int k = 0; k < f; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = fmaf(xs[(rl + 4 * i) * f + k], dyv[i], acc);
+        atomicAdd(dW + static_cast<size_t>(k) * d + c, acc);
+      }
+    }
+  }
+  if (c < d) atomicAdd(dbias + c, bsum);
+}
+
+// =========================================================================================== Adam (Keras semantics)
+// tf.keras.optimizers.Adam (trainer.py:150): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+// w -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)      (eps = 1e-7 outside the root)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   float lr_t, float b1, float b2, float eps, float grad_scale) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// sum of squares (global-norm clipping, single_task_trainer.py:180-183)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) s = fmaf(g[i], g[i], s);
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+// bf16 copy of a Keras-layout kernel without transposing (B operand of the dX = dY . W^T GEMMs), optional column pad
+__global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out,
+                                                          int rows, int cols, int ld_out) {
+  const long long total = static_cast<long long>(rows) * ld_out;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int r = static_cast<int>(i / ld_out), c = static_cast<int>(i % ld_out);
+    out[i] = __float2bfloat16_rn(c < cols ? w[static_cast<size_t>(r) * cols + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- internal launchers
+int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dW, int ldw, int tokens, int in_dim,
+               int out_dim, cudaStream_t st) {
+  FACT_REQUIRE(x_bf16 && dy_bf16 && dW && tokens > 0 && in_dim > 0 && out_dim > 0, FACT_ERR_BAD_SHAPE,
+               "wgrad_gemm: bad arguments");
+  static bool attr_done = false;
+  if (!attr_done) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap tmx, tmy;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmx, x_bf16, tokens, in_dim, ldx, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tmy, dy_bf16, tokens, out_dim, ldy, 64, 64))) return rc;
+  const int tiles_in = (in_dim + WG_BM - 1) / WG_BM, tiles_out = (out_dim + WG_BN - 1) / WG_BN;
+  const int num_kb = (tokens + WG_BK - 1) / WG_BK;
+  int splits = (2 * num_sms()) / (tiles_in * tiles_out);
+  if (splits < 1) splits = 1;
+  if (splits > num_kb) splits = num_kb;
+  const int kb_per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per - 1) / kb_per;
+  dim3 grid(tiles_out, tiles_in, splits);
+  gemm_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(tmx, tmy, dW, ldw, in_dim, out_dim, num_kb, kb_per);
+  FACT_LAUNCH_CHECK("gemm_wgrad_kernel launch");
+  return FACT_OK;
+}
+
+int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* Dv, float* dq_acc,
+                  void* dqkv, int batch, int n, int heads, int head_dim, float scale, cudaStream_t st) {
+  FACT_REQUIRE(qkv && o && d_o && lse && Dv && dq_acc && dqkv, FACT_ERR_BAD_SHAPE, "sdpa_backward: null buffer");
+  FACT_REQUIRE(head_dim == 80 || head_dim == 64 || head_dim == 32 || head_dim == 16, FACT_ERR_UNSUPPORTED,
+               "sdpa_backward: head_dim %d", head_dim);
+  const int d = heads * head_dim;
+  const long long tokens = static_cast<long long>(batch) * n;
+  FACT_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, tokens * d * sizeof(float), st));
+  {
+    const long long warps = tokens * heads;
+    sdpa_bwd_prep_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(
+        static_cast<const bf16*>(o), static_cast<const bf16*>(d_o), Dv, static_cast<int>(tokens), n, heads, head_dim);
+    FACT_LAUNCH_CHECK("sdpa_bwd_prep_kernel");
+  }
+  dim3 grid((n + 63) / 64, heads, batch);
+  const float k_scale = 0.6931471805599453f;  // dK = ln2 * dZ^T q'   (q' = q * scale * log2 e)
+#define FACT_BWD_CASE(DHV)                                                                                         \
+  case DHV: {                                                                                                      \
+    constexpr int smem = (6 * 64 * (DHV + 8) + 64 * 72) * 2 + 4 * 64 * 4;                                          \
+    static bool done = false;                                                                                      \
+    if (!done) {                                                                                                   \
+      FACT_CUDA_CHECK(cudaFuncSetAttribute(sdpa_bwd_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      done = true;                                                                                                 \
+    }                                                                                                              \
+    sdpa_bwd_kernel<DHV><<<grid, 128, smem, st>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_o), lse, \
+                                                  Dv, static_cast<bf16*>(dqkv), dq_acc, n, heads, k_scale);        \
+    break;                                                                                                         \
+  }
+  switch (head_dim) {
+    FACT_BWD_CASE(16)
+    FACT_BWD_CASE(32)
+    FACT_BWD_CASE(64)
+    FACT_BWD_CASE(80)
+  }
+#undef FACT_BWD_CASE
+  FACT_LAUNCH_CHECK("sdpa_bwd_kernel");
+  long long total = tokens * (d / 4);
+  int g2 = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  sdpa_bwd_finish_kernel<<<g2, 256, 0, st>>>(dq_acc, static_cast<bf16*>(dqkv), tokens, d, scale);
+  FACT_LAUNCH_CHECK("sdpa_bwd_finish_kernel");
+  return FACT_OK;
+}
+
+int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, float* dgamma,
+                float* dbeta, int rows, int d, cudaStream_t st) {
+  FACT_REQUIRE(d % 4 == 0 && d <= 1024, FACT_ERR_BAD_SHAPE, "ln_backward: d %d", d);
+  int grid = (rows + 7) / 8;
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
+  ln_bwd_kernel<<<grid, 256, 0, st>>>(x, gamma, dy, dres, dx, dgamma, dbeta, rows, d);
+  FACT_LAUNCH_CHECK("ln_bwd_kernel");
+  return FACT_OK;
+}
+
+int cast_colsum(const float* x, int ldx, void* y, int ldy, float* colsum, int rows, int n, cudaStream_t st) {
+  const int rpb = 64;
+  cast_colsum_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(x, ldx, static_cast<bf16*>(y), ldy, colsum, rows, n, rpb);
+  FACT_LAUNCH_CHECK("cast_colsum_kernel");
+  return FACT_OK;
+}
+
+int colsum_bf16(const void* x, int ldx, float* colsum, int rows, int n, cudaStream_t st) {
+  const int rpb = 64;
+  colsum_bf16_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(static_cast<const bf16*>(x), ldx, colsum, rows, n, rpb);
+  FACT_LAUNCH_CHECK("colsum_bf16_kernel");
+  return FACT_OK;
+}
+
+int slice_rows(const float* src, float* dst, long long rows_dst, int d, int seq_dst, int seq_src, int seq_off,
+               cudaStream_t st) {
+  long long total = rows_dst * (d / 4);
+  int grid = static_cast<int>((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+  slice_rows_kernel<<<grid, 256, 0, st>>>(src, dst, rows_dst, d, seq_dst, seq_src, seq_off);
+  FACT_LAUNCH_CHECK("slice_rows_kernel");
+  return FACT_OK;
+}
+
+int embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dW, float* dbias, float* dpos,
+                   int batch, int n_tok, int f, int d, cudaStream_t st) {
+  const int rows = batch * n_tok;
+  dim3 grid((d + 63) / 64, (rows + 255) / 256);
+  const size_t smem = static_cast<size_t>(64) * f * sizeof(float);
+  static size_t max_set = 0;
+  if (smem > 48 * 1024 && smem > max_set) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    max_set = smem;
+  }
+  embed_bwd_kernel<<<grid, 256, smem, st>>>(x, x_batch_stride, dy, dW, dbias, dpos, rows, n_tok, f, d);
+  FACT_LAUNCH_CHECK("embed_bwd_kernel");
+  return FACT_OK;
+}
+
+int cast_weight(const float* w, void* out, int rows, int cols, int ld_out, cudaStream_t st) {
+  long long total = static_cast<long long>(rows) * ld_out;
+  int grid = static_cast<int>((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+  cast_weight_kernel<<<grid, 256, 0, st>>>(w, static_cast<bf16*>(out), rows, cols, ld_out);
+  FACT_LAUNCH_CHECK("cast_weight_kernel");
+  return FACT_OK;
+}
+
+}  // namespace fact
+
+using namespace fact;
+
+// ------------------------------------------------------------------------------------------- C ABI (training blocks)
+extern "C" int fact_wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dw, int ldw,
+                               int tokens, int in_dim, int out_dim, void* stream) {
+  return wgrad_gemm(x_bf16, ldx, dy_bf16, ldy, dw, ldw, tokens, in_dim, out_dim, as_stream(stream));
+}
+
+extern "C" int fact_sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* d_scratch,
+                                  float* dq_scratch, void* dqkv, int batch, int n, int heads, int head_dim,
+                                  float scale, void* stream) {
+  return sdpa_backward(qkv, o, d_o, lse, d_scratch, dq_scratch, dqkv, batch, n, heads, head_dim, scale,
+                       as_stream(stream));
+}
+
+extern "C" int fact_layernorm_backward(const float* x, const float* gamma, const float* dy, const float* dres,
+                                       float* dx, float* dgamma, float* dbeta, int rows, int d, void* stream) {
+  FACT_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && rows > 0, FACT_ERR_BAD_SHAPE,
+               "fact_layernorm_backward: bad arguments");
+  return ln_backward(x, gamma, dy, dres, dx, dgamma, dbeta, rows, d, as_stream(stream));
+}
+
+extern "C" int fact_embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dw, float* dbias,
+                                   float* dpos, int batch, int n_tok, int f, int d, void* stream) {
+  FACT_REQUIRE(x && dy && dw && dbias && batch > 0 && n_tok > 0 && f > 0 && d > 0, FACT_ERR_BAD_SHAPE,
+               "fact_embed_backward: bad arguments");
+  return embed_backward(x, x_batch_stride, dy, dw, dbias, dpos, batch, n_tok, f, d, as_stream(stream));
+}
+
+extern "C" int fact_cast_colsum(const float* x, int ldx, void* y_bf16, int ldy, float* colsum, int rows, int n,
+                                void* stream) {
+  FACT_REQUIRE(x && rows > 0 && n > 0 && ldy >= n, FACT_ERR_BAD_SHAPE, "fact_cast_colsum: bad arguments");
+  return cast_colsum(x, ldx, y_bf16, ldy, colsum, rows, n, as_stream(stream));
+}
+
+extern "C" int fact_adam_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                              float beta2, float eps, long long step, float grad_scale, void* stream) {
+  FACT_REQUIRE(w && g && m && v && n > 0 && step >= 1, FACT_ERR_BAD_SHAPE, "fact_adam_step: bad arguments");
+  const double t = static_cast<double>(step);
+  const float lr_t = static_cast<float>(lr * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
+                                        (1.0 - pow(static_cast<double>(beta1), t)));
+  long long blocks = (n + 255) / 256;
+  int grid = static_cast<int>(blocks > 16384 ? 16384 : blocks);
+  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+  FACT_LAUNCH_CHECK("adam_kernel");
+  return FACT_OK;
+}
+
+extern "C" int fact_sum_squares(const float* g, long long n, float* out, void* stream) {
+  FACT_REQUIRE(g && out && n > 0, FACT_ERR_BAD_SHAPE, "fact_sum_squares: bad arguments");
+  FACT_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float), as_stream(stream)));
+  long long blocks = (n + 255) / 256;
+  int grid = static_cast<int>(blocks > 4096 ? 4096 : blocks);
+  sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, out);
+  FACT_LAUNCH_CHECK("sumsq_kernel");
+  return FACT_OK;
+}
+
+extern "C" int fact_cast_weight(const float* w_keras, void* out_bf16, int rows, int cols, int ld_out, void* stream) {
+  FACT_REQUIRE(w_keras && out_bf16 && rows > 0 && cols > 0 && ld_out >= cols, FACT_ERR_BAD_SHAPE,
+               "fact_cast_weight: bad arguments");
+  return cast_weight(w_keras, out_bf16, rows, cols, ld_out, as_stream(stream));
+}

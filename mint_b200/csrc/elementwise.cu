@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(SimtArgs p) {
       }
       if (p.pos) x += p.pos[static_cast<size_t>(row % p.pos_seq) * p.n + col];
       if (p.kind == FACT_EPI_BIAS_GELU_SPLIT) x = gelu_tanh(x);
+      if (p.kind == FACT_EPI_BIAS_GELU_SAVE) {
+        const size_t oz = static_cast<size_t>(orow) * p.ldo + col;
+        p.out_lo[oz] = __float2bfloat16_rn(x);
+        p.out_hi[oz] = __float2bfloat16_rn(gelu_tanh(x));
+        continue;
+      }
       if (p.kind == FACT_EPI_BIAS_RESID_F32) x += p.resid[static_cast<size_t>(row) * p.ldr + col];
       const size_t o = static_cast<size_t>(orow) * p.ldo + col;
       if (p.kind == FACT_EPI_SPLIT || p.kind == FACT_EPI_BIAS_GELU_SPLIT) {
@@ -244,8 +250,9 @@ static void fill_epi(SimtArgs& p, const fact_gemm_epilogue* e) {
 
 static int check_epi(const fact_gemm_epilogue* e) {
   FACT_REQUIRE(e != nullptr, FACT_ERR_BAD_SHAPE, "null epilogue");
-  const bool split_out = e->kind == FACT_EPI_SPLIT || e->kind == FACT_EPI_BIAS_GELU_SPLIT;
-  FACT_REQUIRE(e->kind >= 0 && e->kind <= 3, FACT_ERR_UNSUPPORTED, "unknown epilogue kind %d", e->kind);
+  const bool split_out = e->kind == FACT_EPI_SPLIT || e->kind == FACT_EPI_BIAS_GELU_SPLIT ||
+                         e->kind == FACT_EPI_BIAS_GELU_SAVE;
+  FACT_REQUIRE(e->kind >= 0 && e->kind <= 4, FACT_ERR_UNSUPPORTED, "epilogue kind %d not available on the CUDA-core GEMM", e->kind);
   FACT_REQUIRE(split_out ? e->out_hi != nullptr : e->out_f32 != nullptr, FACT_ERR_BAD_SHAPE,
                "epilogue output buffer missing");
   FACT_REQUIRE(e->kind != FACT_EPI_BIAS_RESID_F32 || e->resid, FACT_ERR_BAD_SHAPE, "resid epilogue needs resid");

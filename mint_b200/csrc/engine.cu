@@ -20,8 +20,8 @@ namespace fact {
 int gemm_simt_split(const void* a_hi, const void* a_lo, int lda, const float* w_keras, int m, int n, int k,
                     const fact_gemm_epilogue* epi, cudaStream_t st);
 int step_set(int* p, int v, cudaStream_t st);
-int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
-             int head_dim, int q_rows, cudaStream_t st);
+int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, float* lse, int batch, int n,
+             int heads, int head_dim, int q_rows, cudaStream_t st);
 int step_inc(int* p, cudaStream_t st);
 
 struct Workspace {
@@ -153,7 +153,7 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
   e.scale = static_cast<float>(1.0 / sqrt(static_cast<double>(d)) * 1.4426950408889634);
   e.scale_cols = d;
   if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st))) return rc;
-  if ((rc = sdpa_run(ws.qkv_hi, lo ? ws.qkv_lo : nullptr, ws.ao_hi, lo ? ws.ao_lo : nullptr, batch, seq, H, dh, 1, st)))
+  if ((rc = sdpa_run(ws.qkv_hi, lo ? ws.qkv_lo : nullptr, ws.ao_hi, lo ? ws.ao_lo : nullptr, nullptr, batch, seq, H, dh, 1, st)))
     return rc;
   const int pitch = seq * d;  // row 0 of clip b lives at b * seq * d
   e = fact_gemm_epilogue{};

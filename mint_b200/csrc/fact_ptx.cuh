@@ -312,3 +312,29 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
 }
 
 }  // namespace fact
+
+namespace fact {
+// d/dx of the tanh-form GELU (mint/core/base_model_util.py:94-107)
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float u = k * (x + c * x * x * x);
+  const float e = __expf(2.0f * u);
+  const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * (1.0f + 3.0f * c * x * x);
+}
+// MN-major operand, SWIZZLE_128B: rows are K (128 B = 64 MN elements each), 8-row groups `sbo` bytes apart,
+// successive 64-element MN atoms `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// idesc with selectable major-ness of both operands (bit 15: A MN-major, bit 16: B MN-major)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_maj(int M, int N, int a_mn, int b_mn) {
+  return umma_idesc_bf16_f32(M, N) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16);
+}
+}  // namespace fact

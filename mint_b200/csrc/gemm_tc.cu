@@ -40,6 +40,8 @@ struct EpiArgs {
   int scale_cols;
   int seq_in, seq_out, seq_off;
   int vec_ok;  // all row pitches / base pointers allow 16-byte row-chunk accesses
+  const bf16* aux;  // GELU_GRAD: saved pre-activation
+  int ldaux;
 };
 
 template <int BN, int NPART, int STAGES>
@@ -102,13 +104,67 @@ __device__ __forceinline__ void epilogue_chunk(const float* v, const float4* rv,
     if (!row_ok) return;
     const size_t o = static_cast<size_t>(row) * ep.ldo + col0;
     float x[32];
+    if (EPI == FACT_EPI_BIAS_GELU_SAVE) {  // training forward: h = gelu(z) and z itself, both bf16 (hi only)
+      uint32_t hz[16], zz[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
-        const float b = (fast || col0 + c < N) ? __ldg(ep.bias + col0 + c) : 0.f;
-        x[c] = gelu_tanh(v[c] + b);
+      for (int c = 0; c < 16; ++c) {
+        const float b0 = (fast || col0 + 2 * c < N) ? __ldg(ep.bias + col0 + 2 * c) : 0.f;
+        const float b1 = (fast || col0 + 2 * c + 1 < N) ? __ldg(ep.bias + col0 + 2 * c + 1) : 0.f;
+        const float z0 = v[2 * c] + b0, z1 = v[2 * c + 1] + b1;
+        zz[c] = cvt_bf16x2(z0, z1);
+        hz[c] = cvt_bf16x2(gelu_tanh(z0), gelu_tanh(z1));
+      }
+      if (fast) {
+        uint4* ph = reinterpret_cast<uint4*>(ep.out_hi + o);
+        uint4* pz = reinterpret_cast<uint4*>(ep.out_lo + o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ph[i] = make_uint4(hz[4 * i], hz[4 * i + 1], hz[4 * i + 2], hz[4 * i + 3]);
+          pz[i] = make_uint4(zz[4 * i], zz[4 * i + 1], zz[4 * i + 2], zz[4 * i + 3]);
+        }
       } else {
-        x[c] = (col0 + c < ep.scale_cols) ? v[c] * ep.scale : v[c];
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (col0 + c < N) {
+            const uint32_t hv = hz[c >> 1], zv = zz[c >> 1];
+            ep.out_hi[o + c] = __ushort_as_bfloat16(static_cast<unsigned short>((c & 1) ? hv >> 16 : hv & 0xffff));
+            ep.out_lo[o + c] = __ushort_as_bfloat16(static_cast<unsigned short>((c & 1) ? zv >> 16 : zv & 0xffff));
+          }
+      }
+      return;
+    }
+    if (EPI == FACT_EPI_GELU_GRAD) {  // backward: dz = dh * gelu'(z), z read back as bf16
+      const bf16* zrow = ep.aux + static_cast<size_t>(row) * ep.ldaux + col0;
+      uint32_t zraw[16];
+      if (fast) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 q4 = reinterpret_cast<const uint4*>(zrow)[i];
+          zraw[4 * i] = q4.x; zraw[4 * i + 1] = q4.y; zraw[4 * i + 2] = q4.z; zraw[4 * i + 3] = q4.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const uint32_t a = (col0 + 2 * c < N) ? __bfloat16_as_ushort(zrow[2 * c]) : 0u;
+          const uint32_t b = (col0 + 2 * c + 1 < N) ? __bfloat16_as_ushort(zrow[2 * c + 1]) : 0u;
+          zraw[c] = a | (b << 16);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const uint32_t raw = zraw[c >> 1];
+        const float z = __uint_as_float((c & 1) ? (raw & 0xffff0000u) : (raw << 16));
+        x[c] = v[c] * gelu_tanh_grad(z);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
+          const float b = (fast || col0 + c < N) ? __ldg(ep.bias + col0 + c) : 0.f;
+          x[c] = gelu_tanh(v[c] + b);
+        } else {
+          x[c] = (col0 + c < ep.scale_cols) ? v[c] * ep.scale : v[c];
+        }
       }
     }
     if (fast) {
@@ -605,8 +661,14 @@ static int launch_epi2(int kind, const CUtensorMap& a0, const CUtensorMap& a1, c
       return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_RESID_F32>(a0, a1, b0, b1, m, n, k, ep, st);
     case FACT_EPI_BIAS_F32:
       return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_F32>(a0, a1, b0, b1, m, n, k, ep, st);
+    case FACT_EPI_BIAS_GELU_SAVE:
+      if (NPART == 1) return launch_cfg2<BN, 1, STAGES, FACT_EPI_BIAS_GELU_SAVE>(a0, a1, b0, b1, m, n, k, ep, st);
+      break;
+    case FACT_EPI_GELU_GRAD:
+      if (NPART == 1) return launch_cfg2<BN, 1, STAGES, FACT_EPI_GELU_GRAD>(a0, a1, b0, b1, m, n, k, ep, st);
+      break;
   }
-  set_error("unknown epilogue kind %d", kind);
+  set_error("epilogue kind %d unknown, or a training epilogue (4, 5) used with split (precise) operands", kind);
   return FACT_ERR_UNSUPPORTED;
 }
 
@@ -622,8 +684,14 @@ static int launch_epi(int kind, const CUtensorMap& a0, const CUtensorMap& a1, co
       return launch_cfg<BN, NPART, STAGES, FACT_EPI_BIAS_RESID_F32>(a0, a1, b0, b1, m, n, k, ep, st);
     case FACT_EPI_BIAS_F32:
       return launch_cfg<BN, NPART, STAGES, FACT_EPI_BIAS_F32>(a0, a1, b0, b1, m, n, k, ep, st);
+    case FACT_EPI_BIAS_GELU_SAVE:
+      if (NPART == 1) return launch_cfg<BN, 1, STAGES, FACT_EPI_BIAS_GELU_SAVE>(a0, a1, b0, b1, m, n, k, ep, st);
+      break;
+    case FACT_EPI_GELU_GRAD:
+      if (NPART == 1) return launch_cfg<BN, 1, STAGES, FACT_EPI_GELU_GRAD>(a0, a1, b0, b1, m, n, k, ep, st);
+      break;
   }
-  set_error("unknown epilogue kind %d", kind);
+  set_error("epilogue kind %d unknown, or a training epilogue (4, 5) used with split (precise) operands", kind);
   return FACT_ERR_UNSUPPORTED;
 }
 
@@ -647,11 +715,16 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
   FACT_REQUIRE(m > 0 && n > 0 && k > 0, FACT_ERR_BAD_SHAPE, "fact_gemm: bad shape m=%d n=%d k=%d", m, n, k);
   FACT_REQUIRE((a_lo == nullptr) == (w_lo == nullptr), FACT_ERR_BAD_SHAPE,
                "fact_gemm: a_lo and w_lo must both be given (precise) or both be NULL (bf16)");
-  const bool split_out = epi->kind == FACT_EPI_SPLIT || epi->kind == FACT_EPI_BIAS_GELU_SPLIT;
+  const bool split_out = epi->kind == FACT_EPI_SPLIT || epi->kind == FACT_EPI_BIAS_GELU_SPLIT ||
+                         epi->kind == FACT_EPI_BIAS_GELU_SAVE || epi->kind == FACT_EPI_GELU_GRAD;
   if (split_out) {
     FACT_REQUIRE(epi->out_hi != nullptr && (epi->ldo % 2) == 0, FACT_ERR_BAD_SHAPE,
                  "fact_gemm: split epilogue needs out_hi and an even ldo");
-    FACT_REQUIRE(epi->kind != FACT_EPI_BIAS_GELU_SPLIT || epi->bias, FACT_ERR_BAD_SHAPE, "gelu epilogue needs bias");
+    FACT_REQUIRE((epi->kind != FACT_EPI_BIAS_GELU_SPLIT && epi->kind != FACT_EPI_BIAS_GELU_SAVE) || epi->bias,
+                 FACT_ERR_BAD_SHAPE, "gelu epilogue needs bias");
+    FACT_REQUIRE(epi->kind != FACT_EPI_BIAS_GELU_SAVE || epi->out_lo, FACT_ERR_BAD_SHAPE,
+                 "GELU_SAVE writes the pre-activation through out_lo");
+    FACT_REQUIRE(epi->kind != FACT_EPI_GELU_GRAD || epi->aux, FACT_ERR_BAD_SHAPE, "GELU_GRAD needs aux");
   } else {
     FACT_REQUIRE(epi->out_f32 != nullptr, FACT_ERR_BAD_SHAPE, "fact_gemm: f32 epilogue needs out_f32");
     FACT_REQUIRE(epi->kind != FACT_EPI_BIAS_RESID_F32 || epi->resid, FACT_ERR_BAD_SHAPE, "resid epilogue needs resid");
@@ -669,9 +742,11 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
   ep.seq_in = epi->seq_in;
   ep.seq_out = epi->seq_out;
   ep.seq_off = epi->seq_off;
+  ep.aux = static_cast<const bf16*>(epi->aux);
+  ep.ldaux = epi->ldaux;
   if (split_out)
     ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
-                (!ep.bias || aligned16(ep.bias));
+                (!ep.bias || aligned16(ep.bias)) && (!ep.aux || (aligned16(ep.aux) && ep.ldaux % 8 == 0));
   else
     ep.vec_ok = (ep.ldo % 4 == 0) && aligned16(ep.out_f32) && (!ep.bias || aligned16(ep.bias)) &&
                 (!ep.resid || ((ep.ldr % 4 == 0) && aligned16(ep.resid)));

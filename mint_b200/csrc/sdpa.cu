@@ -22,7 +22,7 @@ constexpr int SDPA_THREADS = 256;
 template <int DH, int NPART>
 __global__ void __launch_bounds__(SDPA_THREADS, (NPART == 1 ? 2 : 1))
 sdpa_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, bf16* __restrict__ o_hi,
-            bf16* __restrict__ o_lo, int N, int H) {
+            bf16* __restrict__ o_lo, float* __restrict__ lse, int N, int H) {
   constexpr int DHP = DH + 8;            // row pitch: 16-B rotation per row -> conflict-free ldmatrix
   constexpr int KSTEPS = DH / 16;
   constexpr int DT = DH / 8;
@@ -233,6 +233,7 @@ sdpa_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, bf
   for (int i = 0; i < 2; ++i) {
     const int row = qb * SDPA_QB + warp * 16 + g + i * 8;
     if (row < N) {
+      if (lse && t == 0) lse[(static_cast<size_t>(b) * H + h) * N + row] = m_run[i] + log2f(l_run[i]);
       const size_t base = (tok0 + row) * D + h * DH + 2 * t;
 #pragma unroll
       for (int dt = 0; dt < DT; ++dt) {
@@ -247,8 +248,8 @@ sdpa_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, bf
 }
 
 template <int DH, int NPART>
-static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int q_rows,
-                       cudaStream_t st) {
+static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, int batch, int n, int heads,
+                       int q_rows, cudaStream_t st) {
   constexpr int smem = 2 * (2 * NPART * SDPA_KB * (DH + 8)) * 2;
   auto kern = sdpa_kernel<DH, NPART>;
   static bool attr_done = false;
@@ -257,13 +258,13 @@ static int launch_sdpa(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int b
     attr_done = true;
   }
   dim3 grid((q_rows + SDPA_QB - 1) / SDPA_QB, heads, batch);
-  kern<<<grid, SDPA_THREADS, smem, st>>>(qh, ql, oh, ol, n, heads);
+  kern<<<grid, SDPA_THREADS, smem, st>>>(qh, ql, oh, ol, lse, n, heads);
   FACT_LAUNCH_CHECK("sdpa_kernel launch");
   return FACT_OK;
 }
 
-int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
-                int q_rows, cudaStream_t st);
+int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, int batch, int n, int heads,
+                int head_dim, int q_rows, cudaStream_t st);
 extern int g_gemm_pair;
 extern int g_ar_prune;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
@@ -292,8 +293,8 @@ extern "C" int fact_set_flag(const char* name, int value) {
 namespace fact {
 
 // q_rows < n: only the first q_rows query rows of every (batch, head) are needed (whole 128-row blocks are computed)
-int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n, int heads,
-             int head_dim, int q_rows, cudaStream_t st) {
+int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, float* lse, int batch, int n,
+             int heads, int head_dim, int q_rows, cudaStream_t st) {
   FACT_REQUIRE(qkv_hi && out_hi, FACT_ERR_BAD_SHAPE, "fact_sdpa: null buffer");
   FACT_REQUIRE((qkv_lo == nullptr) == (out_lo == nullptr), FACT_ERR_BAD_SHAPE,
                "fact_sdpa: qkv_lo and out_lo must both be given (precise) or both NULL (bf16)");
@@ -305,13 +306,13 @@ int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo,
   bf16* ol = static_cast<bf16*>(out_lo);
   const bool precise = qkv_lo != nullptr;
   if (!g_sdpa_legacy) {  // B200-native path: tcgen05 + TMEM-resident scores (head_dim 80, n <= 384)
-    const int rc = sdpa_tc_try(qh, ql, oh, ol, batch, n, heads, head_dim, q_rows, st);
+    const int rc = sdpa_tc_try(qh, ql, oh, ol, lse, batch, n, heads, head_dim, q_rows, st);
     if (rc != FACT_ERR_UNSUPPORTED) return rc;
   }
 #define FACT_SDPA_CASE(DHV)                                                            \
   case DHV:                                                                            \
-    return precise ? launch_sdpa<DHV, 2>(qh, ql, oh, ol, batch, n, heads, q_rows, st)  \
-                   : launch_sdpa<DHV, 1>(qh, ql, oh, ol, batch, n, heads, q_rows, st);
+    return precise ? launch_sdpa<DHV, 2>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)  \
+                   : launch_sdpa<DHV, 1>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st);
   switch (head_dim) {
     FACT_SDPA_CASE(16)
     FACT_SDPA_CASE(32)
@@ -327,5 +328,11 @@ int sdpa_run(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo,
 
 extern "C" int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int batch, int n,
                          int heads, int head_dim, void* stream) {
-  return fact::sdpa_run(qkv_hi, qkv_lo, out_hi, out_lo, batch, n, heads, head_dim, n, fact::as_stream(stream));
+  return fact::sdpa_run(qkv_hi, qkv_lo, out_hi, out_lo, nullptr, batch, n, heads, head_dim, n,
+                        fact::as_stream(stream));
+}
+
+extern "C" int fact_sdpa_lse(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, float* lse, int batch,
+                             int n, int heads, int head_dim, void* stream) {
+  return fact::sdpa_run(qkv_hi, qkv_lo, out_hi, out_lo, lse, batch, n, heads, head_dim, n, fact::as_stream(stream));
 }

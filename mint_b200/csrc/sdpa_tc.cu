@@ -41,7 +41,8 @@ struct SdpaTcCfg {
 template <int NPART>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-               bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, int N, int H, int q_blocks, int num_tiles) {
+               bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, float* __restrict__ lse, int N, int H, int q_blocks,
+               int num_tiles) {
   using Cfg = SdpaTcCfg<NPART>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -243,6 +244,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (row < N) {
+        if (lse) lse[(static_cast<size_t>(b) * H + h) * N + row] = mx + log2f(lsum);
         const size_t base = (static_cast<size_t>(b) * N + row) * D + h * TC_DH;
         uint32_t hh[TC_DH / 2], ll[TC_DH / 2];
 #pragma unroll
@@ -274,8 +276,8 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 }
 
 template <int NPART>
-static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads,
-                          int q_rows, cudaStream_t st) {
+static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, int batch, int n,
+                          int heads, int q_rows, cudaStream_t st) {
   using Cfg = SdpaTcCfg<NPART>;
   auto kern = sdpa_tc_kernel<NPART>;
   static bool attr_done = false;
@@ -295,21 +297,21 @@ static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, in
   const int q_blocks = (q_rows + TC_QB - 1) / TC_QB;
   const int num_tiles = q_blocks * heads * batch;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmh, tml, oh, ol, n, heads, q_blocks, num_tiles);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmh, tml, oh, ol, lse, n, heads, q_blocks, num_tiles);
   FACT_LAUNCH_CHECK("sdpa_tc_kernel launch");
   return FACT_OK;
 }
 
 // tcgen05 path: head_dim 80, n <= 384, 16-byte aligned buffers.  Returns FACT_ERR_UNSUPPORTED (without setting an
 // error) when the shape is outside that envelope so that fact_sdpa falls back to the generic mma.sync kernel.
-int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, int batch, int n, int heads, int head_dim,
-                int q_rows, cudaStream_t st) {
+int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, int batch, int n, int heads,
+                int head_dim, int q_rows, cudaStream_t st) {
   if (head_dim != TC_DH || n > TC_MAXBLK * TC_KB) return FACT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(qh) | reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ql) |
        reinterpret_cast<uintptr_t>(ol)) & 15)
     return FACT_ERR_UNSUPPORTED;
-  return ql ? launch_sdpa_tc<2>(qh, ql, oh, ol, batch, n, heads, q_rows, st)
-            : launch_sdpa_tc<1>(qh, ql, oh, ol, batch, n, heads, q_rows, st);
+  return ql ? launch_sdpa_tc<2>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)
+            : launch_sdpa_tc<1>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st);
 }
 
 }  // namespace fact

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfact_sm100.so")
 
 MODE_PRECISE, MODE_BF16, MODE_FP32_SIMT = 0, 1, 2
 MODES = {"precise": MODE_PRECISE, "bf16": MODE_BF16, "fp32_simt": MODE_FP32_SIMT}
-EPI_SPLIT, EPI_BIAS_GELU_SPLIT, EPI_BIAS_RESID_F32, EPI_BIAS_F32 = 0, 1, 2, 3
+EPI_SPLIT, EPI_BIAS_GELU_SPLIT, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_BIAS_GELU_SAVE, EPI_GELU_GRAD = 0, 1, 2, 3, 4, 5
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -40,7 +40,7 @@ class Weights(C.Structure):
 class GemmEpilogue(C.Structure):
     _fields_ = [("kind", _i), ("out_f32", _vp), ("out_hi", _vp), ("out_lo", _vp), ("ldo", _i), ("bias", _vp),
                 ("resid", _vp), ("ldr", _i), ("scale", _f), ("scale_cols", _i), ("seq_in", _i), ("seq_out", _i),
-                ("seq_off", _i)]
+                ("seq_off", _i), ("aux", _vp), ("ldaux", _i)]
 
 
 # symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/fact_sm100.h
