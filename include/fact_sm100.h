@@ -71,6 +71,11 @@ typedef struct fact_layer_weights {
   const float* wo_f32;     /* [d, d]  */
   const float* w1_f32;     /* [d, ff] */
   const float* w2_f32;     /* [ff, d] */
+  /* Keras-layout ([in, out]) bf16 copies: K-major B operands of the backward dX = dY . W^T GEMMs (training only) */
+  const void* wqkv_kl;     /* bf16 [d, 3d] */
+  const void* wo_kl;       /* bf16 [d, d]  */
+  const void* w1_kl;       /* bf16 [d, ff] */
+  const void* w2_kl;       /* bf16 [ff, d] */
 } fact_layer_weights;
 
 typedef struct fact_dims {
@@ -102,7 +107,20 @@ typedef struct fact_weights {
   const float* out_b;                      /* [out_dim] */
   const void* out_w_hi;                    /* bf16 [out_dim, d] packed, for the all-rows head */
   const void* out_w_lo;
+  const void* out_w_kl;                    /* bf16 [d, pad64(out_dim)] Keras layout, zero padded (training only) */
 } fact_weights;
+
+/* fp32 gradients, same shapes and Keras layout as the master weights (single_task_trainer.py:163-178). */
+typedef struct fact_layer_grads {
+  float *ln1_gamma, *ln1_beta, *wqkv, *wo, *bo, *ln2_gamma, *ln2_beta, *w1, *b1, *w2, *b2;
+} fact_layer_grads;
+
+typedef struct fact_grads {
+  const fact_layer_grads* motion_layers; /* host arrays, like fact_weights */
+  const fact_layer_grads* audio_layers;
+  const fact_layer_grads* cross_layers;
+  float *motion_embed_w, *motion_embed_b, *motion_pos, *audio_embed_w, *audio_embed_b, *audio_pos, *out_w, *out_b;
+} fact_grads;
 
 /* Pack a Keras-layout fp32 kernel [k_in, n_out] into K-major bf16 [n_out, k_in]: hi = bf16(w), lo = bf16(w-hi).
  * lo may be NULL. */
@@ -240,6 +258,16 @@ FACT_API int fact_adam_step(float* w, const float* g, float* m, float* v, long l
 
 /* *out = sum g^2 (for clip_by_global_norm, single_task_trainer.py:180-183). */
 FACT_API int fact_sum_squares(const float* g, long long n, float* out, void* stream);
+
+FACT_API size_t fact_train_workspace_bytes(const fact_dims* dims, int batch);
+
+/* One replica's train step up to the gradients (single_task_trainer.py:145-178): forward with saved activations,
+ * *loss_out = FACTModel.loss(target, pred) (unscaled), gradients of loss * loss_scale ACCUMULATED into `g` (zero the
+ * gradient buffers first; loss_scale = 1 / num_replicas as in :157-158).  bf16 products, fp32 everything else.
+ * target: [B, target_len, out_dim]. */
+FACT_API int fact_train_step(const fact_dims* dims, const fact_weights* w, const fact_grads* g, const float* motion,
+                             const float* audio, const float* target, int target_len, int batch, float loss_scale,
+                             float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

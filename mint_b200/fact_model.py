@@ -44,8 +44,13 @@ class FACTModel:
         self.use_graph = use_graph
         self.global_step = None        # set by trainer / evaluator (trainer.py:151, evaluator.py:57)
         self.losses = []               # Keras regularisation losses: none in FACT
-        self._params: dict[str, torch.Tensor] = {}
+        self._params: dict[str, torch.Tensor] = {}     # views into self._flat (one bucket: one NCCL all-reduce)
+        self._grads: dict[str, torch.Tensor] | None = None
+        self._flat: torch.Tensor | None = None
+        self._grad_flat: torch.Tensor | None = None
         self._packed: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}
+        self._keras_bf16: dict[str, torch.Tensor] = {}  # Keras-layout bf16 copies (backward dX GEMMs), training only
+        self._train_ws: torch.Tensor | None = None
         self._ws: dict[tuple, torch.Tensor] = {}
         self._side_stream = None
         self._step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -72,15 +77,23 @@ class FACTModel:
         extra = set(weights) - set(shapes)
         if missing or extra:
             raise KeyError(f"weight names mismatch: missing {sorted(missing)[:3]} extra {sorted(extra)[:3]}")
+        if self._flat is None:
+            self._offsets, off = {}, 0
+            for name, shp in shapes.items():
+                n = 1
+                for v in shp:
+                    n *= v
+                self._offsets[name] = (off, n)
+                off += (n + 3) // 4 * 4                      # keep every tensor 16-byte aligned inside the bucket
+            self._flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+            for name, shp in shapes.items():
+                o, n = self._offsets[name]
+                self._params[name] = self._flat[o:o + n].view(shp)
         for name, shp in shapes.items():
             t = torch.as_tensor(weights[name]).to(torch.float32)
             if tuple(t.shape) != tuple(shp):
                 raise ValueError(f"{name}: shape {tuple(t.shape)} != {shp}")
-            t = t.to(self.device).contiguous()
-            if name in self._params:
-                self._params[name].copy_(t)
-            else:
-                self._params[name] = t.clone()
+            self._params[name].copy_(t.to(self.device))
         self.repack()
 
     def repack(self) -> None:
@@ -97,6 +110,10 @@ class FACTModel:
                 hi, lo = self._packed[name]
                 lib.check(self._lib.fact_pack_weight(p.data_ptr(), hi.data_ptr(), lo.data_ptr(), k_in, n_out, st),
                           "fact_pack_weight")
+                if name in self._keras_bf16:
+                    kl = self._keras_bf16[name]
+                    lib.check(self._lib.fact_cast_weight(p.data_ptr(), kl.data_ptr(), k_in, n_out, kl.shape[1], st),
+                              "fact_cast_weight")
         self._build_tables()
 
     def _build_tables(self) -> None:
@@ -107,12 +124,15 @@ class FACTModel:
             g = lambda s: P[f"{prefix}/{s}"].data_ptr()
             hi = lambda s: K[f"{prefix}/{s}"][0].data_ptr()
             lo = lambda s: K[f"{prefix}/{s}"][1].data_ptr() if precise else None
+            kl = lambda s: (self._keras_bf16[f"{prefix}/{s}"].data_ptr()
+                            if f"{prefix}/{s}" in self._keras_bf16 else None)
             return lib.LayerWeights(
                 g("attn/norm/gamma"), g("attn/norm/beta"), hi("attn/to_qkv/kernel"), lo("attn/to_qkv/kernel"),
                 hi("attn/to_out/kernel"), lo("attn/to_out/kernel"), g("attn/to_out/bias"),
                 g("mlp/norm/gamma"), g("mlp/norm/beta"), hi("mlp/dense_0/kernel"), lo("mlp/dense_0/kernel"),
                 g("mlp/dense_0/bias"), hi("mlp/dense_1/kernel"), lo("mlp/dense_1/kernel"), g("mlp/dense_1/bias"),
-                g("attn/to_qkv/kernel"), g("attn/to_out/kernel"), g("mlp/dense_0/kernel"), g("mlp/dense_1/kernel"))
+                g("attn/to_qkv/kernel"), g("attn/to_out/kernel"), g("mlp/dense_0/kernel"), g("mlp/dense_1/kernel"),
+                kl("attn/to_qkv/kernel"), kl("attn/to_out/kernel"), kl("mlp/dense_0/kernel"), kl("mlp/dense_1/kernel"))
 
         d = self.dims
         self._lw_motion = (lib.LayerWeights * d.motion.layers)(
@@ -128,7 +148,8 @@ class FACTModel:
             P["motion_pos_embedding"].data_ptr(),
             P["audio_linear_embedding/kernel"].data_ptr(), P["audio_linear_embedding/bias"].data_ptr(),
             P["audio_pos_embedding"].data_ptr(),
-            P[ok].data_ptr(), P[ob].data_ptr(), K[ok][0].data_ptr(), K[ok][1].data_ptr() if precise else None)
+            P[ok].data_ptr(), P[ob].data_ptr(), K[ok][0].data_ptr(), K[ok][1].data_ptr() if precise else None,
+            self._keras_bf16[ok].data_ptr() if ok in self._keras_bf16 else None)
 
     # ------------------------------------------------------------------ plumbing
     def _workspace(self, batch: int):
@@ -238,6 +259,90 @@ class FACTModel:
 
     def compute_motion_generation_loss(self, pred_tensors, target_tensors):
         return self.loss(target_tensors, pred_tensors)
+
+    # ------------------------------------------------------------------ training (single_task_trainer.py:138-187)
+    @property
+    def flat_parameters(self) -> torch.Tensor:
+        """All trainable variables as ONE fp32 bucket (the named variables are views into it)."""
+        return self._flat
+
+    @property
+    def flat_gradients(self) -> torch.Tensor:
+        self._ensure_training_state()
+        return self._grad_flat
+
+    def gradients(self) -> dict:
+        self._ensure_training_state()
+        return self._grads
+
+    def _ensure_training_state(self) -> None:
+        if self._grad_flat is not None:
+            return
+        self._grad_flat = torch.zeros_like(self._flat)
+        self._grads = {}
+        for name, p in self._params.items():
+            o, n = self._offsets[name]
+            self._grads[name] = self._grad_flat[o:o + n].view(p.shape)
+        pad64 = lambda v: (v + 63) // 64 * 64
+        for name, p in self._params.items():
+            if name.endswith("/kernel") and "linear_embedding" not in name:
+                cols = p.shape[1]
+                ld = pad64(cols) if name == "cross_modal_layer/output/kernel" else cols
+                self._keras_bf16[name] = torch.zeros((p.shape[0], ld), dtype=_TORCH_BF16, device=self.device)
+        self.repack()
+        self._build_grad_tables()
+
+    def _build_grad_tables(self) -> None:
+        G, d = self._grads, self.dims
+
+        def layer(prefix: str) -> lib.LayerGrads:
+            g = lambda s: G[f"{prefix}/{s}"].data_ptr()
+            return lib.LayerGrads(g("attn/norm/gamma"), g("attn/norm/beta"), g("attn/to_qkv/kernel"),
+                                  g("attn/to_out/kernel"), g("attn/to_out/bias"), g("mlp/norm/gamma"),
+                                  g("mlp/norm/beta"), g("mlp/dense_0/kernel"), g("mlp/dense_0/bias"),
+                                  g("mlp/dense_1/kernel"), g("mlp/dense_1/bias"))
+
+        self._lg_motion = (lib.LayerGrads * d.motion.layers)(
+            *[layer(f"motion_transformer/layer_{i}") for i in range(d.motion.layers)])
+        self._lg_audio = (lib.LayerGrads * d.audio.layers)(
+            *[layer(f"audio_transformer/layer_{i}") for i in range(d.audio.layers)])
+        self._lg_cross = (lib.LayerGrads * d.cross_layers)(
+            *[layer(f"cross_modal_layer/transformer/layer_{i}") for i in range(d.cross_layers)])
+        self._cg = lib.Grads(
+            self._lg_motion, self._lg_audio, self._lg_cross,
+            G["motion_linear_embedding/kernel"].data_ptr(), G["motion_linear_embedding/bias"].data_ptr(),
+            G["motion_pos_embedding"].data_ptr(),
+            G["audio_linear_embedding/kernel"].data_ptr(), G["audio_linear_embedding/bias"].data_ptr(),
+            G["audio_pos_embedding"].data_ptr(),
+            G["cross_modal_layer/output/kernel"].data_ptr(), G["cross_modal_layer/output/bias"].data_ptr())
+
+    def forward_backward(self, inputs: dict, target, loss_scale: float = 1.0) -> torch.Tensor:
+        """One replica's forward + backward (single_task_trainer.py:145-178): returns FACTModel.loss(target, pred)
+        and leaves d(loss * loss_scale)/d(variable) in `flat_gradients` (zeroed first).  bf16 products, fp32 stats."""
+        self._ensure_training_state()
+        d = self.dims
+        motion = self._to_dev(inputs["motion_input"], d.motion.feature_dim, "motion_input")
+        audio = self._to_dev(inputs["audio_input"], d.audio.feature_dim, "audio_input")
+        target = self._to_dev(target, d.out_dim, "target")
+        if motion.shape[1] != d.motion.seq_len or audio.shape[1] != d.audio.seq_len:
+            raise ValueError("sequence lengths must match the position tables")
+        batch = motion.shape[0]
+        if audio.shape[0] != batch or target.shape[0] != batch:
+            raise ValueError("batch sizes differ")
+        need = self._lib.fact_train_workspace_bytes(C.byref(self._cdims), batch)
+        if self._train_ws is None or self._train_ws.numel() < need + 1024:
+            self._train_ws = None
+            self._train_ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        base = (self._train_ws.data_ptr() + 1023) & ~1023
+        loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._grad_flat.zero_()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            lib.check(self._lib.fact_train_step(
+                C.byref(self._cdims), C.byref(self._cw), C.byref(self._cg), motion.data_ptr(), audio.data_ptr(),
+                target.data_ptr(), target.shape[1], batch, float(loss_scale), loss.data_ptr(), base,
+                self._train_ws.numel() - (base - self._train_ws.data_ptr()), st), "fact_train_step")
+        return loss
 
     def get_metrics(self, eval_config):
         """Metrics are computed offline in the reference (fact_model.py:138-141)."""

@@ -21,7 +21,13 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 class LayerWeights(C.Structure):
     _fields_ = [(n, _vp) for n in (
         "ln1_gamma", "ln1_beta", "wqkv_hi", "wqkv_lo", "wo_hi", "wo_lo", "bo", "ln2_gamma", "ln2_beta",
-        "w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "wqkv_f32", "wo_f32", "w1_f32", "w2_f32")]
+        "w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "wqkv_f32", "wo_f32", "w1_f32", "w2_f32",
+        "wqkv_kl", "wo_kl", "w1_kl", "w2_kl")]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [(n, _vp) for n in (
+        "ln1_gamma", "ln1_beta", "wqkv", "wo", "bo", "ln2_gamma", "ln2_beta", "w1", "b1", "w2", "b2")]
 
 
 class Dims(C.Structure):
@@ -34,7 +40,14 @@ class Weights(C.Structure):
     _fields_ = [("motion_layers", C.POINTER(LayerWeights)), ("audio_layers", C.POINTER(LayerWeights)),
                 ("cross_layers", C.POINTER(LayerWeights))] + [(n, _vp) for n in (
         "motion_embed_w", "motion_embed_b", "motion_pos", "audio_embed_w", "audio_embed_b", "audio_pos",
-        "out_w", "out_b", "out_w_hi", "out_w_lo")]
+        "out_w", "out_b", "out_w_hi", "out_w_lo", "out_w_kl")]
+
+
+class Grads(C.Structure):
+    _fields_ = [("motion_layers", C.POINTER(LayerGrads)), ("audio_layers", C.POINTER(LayerGrads)),
+                ("cross_layers", C.POINTER(LayerGrads))] + [(n, _vp) for n in (
+        "motion_embed_w", "motion_embed_b", "motion_pos", "audio_embed_w", "audio_embed_b", "audio_pos",
+        "out_w", "out_b")]
 
 
 class GemmEpilogue(C.Structure):

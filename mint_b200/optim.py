@@ -1,0 +1,94 @@
+"""Keras-semantics Adam on the model's flat parameter bucket + the reference's ManualStepping schedule.
+
+tf.keras.optimizers.Adam(learning_rate) as used at trainer.py:150 (beta_1 0.9, beta_2 0.999, epsilon 1e-7, epsilon
+outside the square root, bias correction folded into the step size); ManualStepping: learning_schedules.py:19-67.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+
+
+class ManualStepping:
+    """Piecewise-constant rate: rates[i] applies for boundaries[i-1] <= step < boundaries[i]; with warmup the first
+    interval ramps linearly from rates[0] to rates[1] (learning_schedules.py:19-67)."""
+
+    def __init__(self, boundaries, rates, warmup: bool = False):
+        if any(b < 0 for b in boundaries) or any(int(b) != b for b in boundaries):
+            raise ValueError("boundaries must be a list of positive integers")
+        if any(b2 <= b1 for b1, b2 in zip(boundaries, boundaries[1:])):
+            raise ValueError("Entries in boundaries must be strictly increasing.")
+        if len(rates) != len(boundaries) + 1:
+            raise ValueError("Number of provided learning rates must exceed number of boundary points by exactly 1.")
+        if boundaries and boundaries[0] == 0:
+            raise ValueError("First step cannot be zero.")
+        self.boundaries, self.rates, self.warmup = list(boundaries), [float(r) for r in rates], warmup
+
+    def __call__(self, step: int) -> float:
+        bounds, rates = self.boundaries, self.rates
+        if self.warmup and bounds:
+            slope = (rates[1] - rates[0]) / bounds[0]
+            ramp = [rates[0] + slope * i for i in range(bounds[0])]
+            bounds = list(range(bounds[0])) + bounds
+            rates = ramp + rates[1:]
+        else:
+            bounds = [0] + bounds
+        idx = 0
+        for i, b in enumerate(bounds):
+            if step >= b:
+                idx = i
+        return rates[idx]
+
+
+def learning_rate_from_config(train_config):
+    """train.proto LearningRate oneof -> callable(step) (trainer.py:49-96)."""
+    lr = train_config.learning_rate
+    kind = lr.WhichOneof("learning_rate")
+    if kind == "constant_learning_rate":
+        rate = lr.constant_learning_rate.learning_rate
+        return lambda step: rate
+    if kind == "manual_step_learning_rate":
+        cfg = lr.manual_step_learning_rate
+        if not cfg.schedule:
+            raise ValueError("Empty learning rate schedule.")
+        return ManualStepping([s.step for s in cfg.schedule],
+                              [cfg.initial_learning_rate] + [s.learning_rate for s in cfg.schedule], cfg.warmup)
+    raise ValueError("Learning_rate %s not supported." % kind)
+
+
+class Adam:
+    def __init__(self, model, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.model = model
+        self.learning_rate = learning_rate          # float or callable(step)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+        self.iterations = 0                         # optimizer.iterations (checkpoint step counter, trainer.py:171)
+        flat = model.flat_parameters
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self._lib = lib.load()
+
+    def current_lr(self) -> float:
+        lr = self.learning_rate
+        return float(lr(self.iterations)) if callable(lr) else float(lr)
+
+    def apply_gradients(self, grad_scale: float = 1.0) -> None:
+        """w -= lr_t * m / (sqrt(v) + eps) on the whole bucket, then refresh the bf16 operand copies."""
+        model = self.model
+        flat, grad = model.flat_parameters, model.flat_gradients
+        lr = self.current_lr()
+        self.iterations += 1
+        with torch.cuda.device(model.device):
+            st = torch.cuda.current_stream(model.device).cuda_stream
+            lib.check(self._lib.fact_adam_step(flat.data_ptr(), grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                               flat.numel(), lr, self.beta_1, self.beta_2, self.epsilon,
+                                               self.iterations, float(grad_scale), st), "fact_adam_step")
+        model.repack()
+
+    def state_dict(self):
+        return {"iterations": self.iterations, "m": self.m, "v": self.v}
+
+    def load_state_dict(self, sd):
+        self.iterations = int(sd["iterations"])
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])

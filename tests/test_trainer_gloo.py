@@ -1,0 +1,77 @@
+"""N>1 host logic on CPU (gloo, world_size 2): the trainer's loss scaling, clip-before-reduce order and the single
+SUM all-reduce of the flat gradient bucket (mint/ctl/single_task_trainer.py:157-158, 180-187); clip sharding helper."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mint_b200 import parallel
+from mint_b200.trainer import SingleTaskTrainer
+
+
+class _FakeModel:
+    """Stands in for FACTModel: per-rank gradient = (rank + 1) * base * loss_scale."""
+
+    def __init__(self, rank):
+        self.rank = rank
+        self.flat_parameters = torch.zeros(8)
+        self.flat_gradients = torch.zeros(8)
+        self.global_step = None
+        self.device = torch.device("cpu")
+
+    def forward_backward(self, inputs, target, loss_scale=1.0):
+        assert "target" not in inputs                      # the label is popped before the call (:145)
+        self.flat_gradients.copy_((self.rank + 1) * torch.arange(1.0, 9.0) * loss_scale)
+        return torch.tensor(float(self.rank + 1))
+
+
+class _FakeOpt:
+    def __init__(self, model):
+        self.model, self.iterations, self.seen = model, 0, None
+
+    def apply_gradients(self, grad_scale=1.0):
+        self.seen = self.model.flat_gradients.clone()
+        self.iterations += 1
+
+    def current_lr(self):
+        return 1e-4
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = _FakeModel(rank)
+    opt = _FakeOpt(model)
+    tr = SingleTaskTrainer([], "target", model, optimizer=opt)
+    loss = tr.train_step({"motion_input": 0, "audio_input": 0, "target": 1})
+    # SUM over ranks of (rank+1)/world * base = mean over ranks = 1.5 * base
+    ok = torch.allclose(opt.seen, 1.5 * torch.arange(1.0, 9.0)) and float(loss) == rank + 1 and model.global_step == 1
+    shard = parallel.shard_clips(11, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, shard)
+    flat = sorted(i for s in gathered for i in s)
+    ok = ok and flat == list(range(11)) and abs(len(gathered[0]) - len(gathered[1])) <= 1
+    t = parallel.max_over_ranks(float(rank + 3))
+    ok = ok and t == 4.0
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_shard_clips_single_process():
+    assert parallel.shard_clips(5, 0, 1) == [0, 1, 2, 3, 4]
+    assert [len(parallel.shard_clips(10, r, 4)) for r in range(4)] == [3, 3, 2, 2]
+    assert parallel.max_over_ranks(2.5) == 2.5
