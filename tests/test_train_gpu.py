@@ -107,3 +107,19 @@ def test_clip_scale(cuda, fact_lib):
     m.forward_backward(tin, tin["target"])
     norm = float(m.flat_gradients.double().norm())
     assert abs(clip_scale(m, norm / 2) - 0.5) < 1e-3 and clip_scale(m, norm * 2) == 1.0
+
+
+def test_evaluator_writes_reference_layout(cuda, fact_lib, tmp_path):
+    """single_task_evaluator.py:64-89: [seed | generated] per clip saved as {motion_name}_{audio_name}.npy."""
+    from mint_b200.evaluator import SingleTaskEvaluator
+    dims = oracle_dims(audio_dim=35, **SMALL)
+    m = FACTModel(make_config(**SMALL), is_training=True)
+    inp = O.synthetic_inputs(dims, batch=2, audio_len=dims.audio_seq + 4, seed=8)
+    batch = {"motion_input": torch.from_numpy(inp["motion_input"]).float(),
+             "audio_input": torch.from_numpy(inp["audio_input"]).float(),
+             "motion_name": [b"gBR_sBM_c01", b"gPO_sFM_c02"], "audio_name": ["mBR0", "mPO1"]}
+    ev = SingleTaskEvaluator([batch], m, output_dir=str(tmp_path), steps=1200)
+    assert ev.evaluate(-1) == {"clips_batches": 1}
+    a = np.load(tmp_path / "gBR_sBM_c01_mBR0.npy")
+    assert a.shape == (dims.motion_seq + 5, 225) and np.allclose(a[:dims.motion_seq], inp["motion_input"][0], atol=1e-6)
+    assert (tmp_path / "gPO_sFM_c02_mPO1.npy").exists()
