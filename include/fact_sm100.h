@@ -236,9 +236,10 @@ FACT_API int fact_sdpa_backward(const void* qkv, const void* o, const void* d_o,
                                 float* dq_scratch, void* dqkv, int batch, int n, int heads, int head_dim, float scale,
                                 void* stream);
 
-/* dx = dres + d LayerNorm(x; gamma)^T dy (dres may be NULL); dgamma / dbeta accumulate (zero them first). */
+/* dx = dres + d LayerNorm(x; gamma)^T dy (dres may be NULL, dx may alias dres); dgamma / dbeta accumulate (zero them
+ * first).  stats_scratch: 4 * rows floats (16-byte aligned). */
 FACT_API int fact_layernorm_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx,
-                                     float* dgamma, float* dbeta, int rows, int d, void* stream);
+                                     float* dgamma, float* dbeta, float* stats_scratch, int rows, int d, void* stream);
 
 /* Gradients of fact_embed: dw[f, d] += x^T dy, dbias[d] += colsum(dy), dpos[n_tok, d] += sum over clips (may be NULL). */
 FACT_API int fact_embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dw, float* dbias,

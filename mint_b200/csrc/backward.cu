@@ -344,99 +344,99 @@ __global__ void __launch_bounds__(256) sdpa_bwd_finish_kernel(const float* __res
 }
 
 // =========================================================================================== LayerNorm backward
-// dx_out = dres + LN'(x; gamma)^T dy ; per-block partial dgamma / dbeta reduced with atomics.  One warp per row,
-// each block walks rows blockIdx.x, +gridDim.x ...  (d <= 1024, d % 4 == 0)
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ dy, const float* __restrict__ dres,
-                                                     float* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int rows, int d) {
-  __shared__ float sg[1024], sb[1024];
-  for (int i = threadIdx.x; i < d; i += 256) sg[i] = sb[i] = 0.f;
-  __syncthreads();
+// Two bandwidth-shaped passes (the one-pass version needed 154 registers -> 8 warps/SM and ran at 1/4 of HBM speed):
+//  (1) ln_bwd_stats_kernel: one warp per row -> stats[row] = {mean, rstd, mean(g*dy), mean(g*dy*xhat)}
+//  (2) ln_bwd_apply_kernel: thread = one float4 column group, block = a slab of rows: dx = dres + rstd*(g*dy - m1 -
+//      xhat*m2), dgamma / dbeta partial sums live in 8 registers and leave through one atomicAdd per column per block.
+__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ dy, float4* __restrict__ stats,
+                                                           int rows, int d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
   const int nv = d >> 2;
-  float4 ag[8], ab[8];
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
+  const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * d);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 v[8];
+  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
-    const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * d);
-    float4 v[8], gdy[8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = lane + i * 32;
-      v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / d;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (lane + i * 32 < nv) {
-        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / d + 1e-5f);
-    float s1 = 0.f, s2 = 0.f;  // sum(g*dy), sum(g*dy*xhat)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = lane + i * 32;
-      if (idx < nv) {
-        const float4 dyv = yr[idx];
-        const float4 gg = *reinterpret_cast<const float4*>(gamma + idx * 4);
-        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
-        gdy[i] = make_float4(gg.x * dyv.x, gg.y * dyv.y, gg.z * dyv.z, gg.w * dyv.w);
-        s1 += (gdy[i].x + gdy[i].y) + (gdy[i].z + gdy[i].w);
-        s2 += (gdy[i].x * v[i].x + gdy[i].y * v[i].y) + (gdy[i].z * v[i].z + gdy[i].w * v[i].w);
-        ag[i].x += dyv.x * v[i].x; ag[i].y += dyv.y * v[i].y; ag[i].z += dyv.z * v[i].z; ag[i].w += dyv.w * v[i].w;
-        ab[i].x += dyv.x; ab[i].y += dyv.y; ab[i].z += dyv.z; ab[i].w += dyv.w;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    const float m1 = s1 / d, m2 = s2 / d;
-    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * d) : nullptr;
-    float4* outr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * d);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = lane + i * 32;
-      if (idx < nv) {
-        float4 o4;
-        o4.x = rstd * (gdy[i].x - m1 - v[i].x * m2);
-        o4.y = rstd * (gdy[i].y - m1 - v[i].y * m2);
-        o4.z = rstd * (gdy[i].z - m1 - v[i].z * m2);
-        o4.w = rstd * (gdy[i].w - m1 - v[i].w * m2);
-        if (rr) {
-          const float4 r4 = rr[idx];
-          o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
-        }
-        outr[idx] = o4;
-      }
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (lane + i * 32 < nv) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / d + 1e-5f);
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
-      atomicAdd(&sg[idx * 4 + 0], ag[i].x); atomicAdd(&sg[idx * 4 + 1], ag[i].y);
-      atomicAdd(&sg[idx * 4 + 2], ag[i].z); atomicAdd(&sg[idx * 4 + 3], ag[i].w);
-      atomicAdd(&sb[idx * 4 + 0], ab[i].x); atomicAdd(&sb[idx * 4 + 1], ab[i].y);
-      atomicAdd(&sb[idx * 4 + 2], ab[i].z); atomicAdd(&sb[idx * 4 + 3], ab[i].w);
+      const float4 dyv = yr[idx];
+      const float4 gg = __ldg(g4 + idx);
+      const float a0 = gg.x * dyv.x, a1 = gg.y * dyv.y, a2 = gg.z * dyv.z, a3 = gg.w * dyv.w;
+      s1 += (a0 + a1) + (a2 + a3);
+      s2 += (a0 * v[i].x + a1 * v[i].y) + (a2 * v[i].z + a3 * v[i].w);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += 256) {
-    atomicAdd(dgamma + i, sg[i]);
-    atomicAdd(dbeta + i, sb[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
+  if (lane == 0) stats[row] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
+}
+
+constexpr int LN_ROWS_PER_BLOCK = 32;
+__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ dy, const float* __restrict__ dres,
+                                                           const float4* __restrict__ stats, float* __restrict__ dx,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           int rows, int d) {
+  const int nv = d >> 2;
+  const int cg = threadIdx.x;  // column group (d <= 1024 -> nv <= 256)
+  if (cg >= nv) return;
+  const int r0 = blockIdx.x * LN_ROWS_PER_BLOCK;
+  const int r1 = min(rows, r0 + LN_ROWS_PER_BLOCK);
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + cg);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const size_t off = static_cast<size_t>(r) * nv + cg;
+    const float4 xv = reinterpret_cast<const float4*>(x)[off];
+    const float4 dyv = reinterpret_cast<const float4*>(dy)[off];
+    const float4 st = __ldg(stats + r);  // mean, rstd, m1, m2
+    float4 xh;
+    xh.x = (xv.x - st.x) * st.y; xh.y = (xv.y - st.x) * st.y; xh.z = (xv.z - st.x) * st.y; xh.w = (xv.w - st.x) * st.y;
+    float4 o;
+    o.x = st.y * (gg.x * dyv.x - st.z - xh.x * st.w);
+    o.y = st.y * (gg.y * dyv.y - st.z - xh.y * st.w);
+    o.z = st.y * (gg.z * dyv.z - st.z - xh.z * st.w);
+    o.w = st.y * (gg.w * dyv.w - st.z - xh.w * st.w);
+    if (dres) {
+      const float4 rr = reinterpret_cast<const float4*>(dres)[off];
+      o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+    }
+    reinterpret_cast<float4*>(dx)[off] = o;
+    ag.x += dyv.x * xh.x; ag.y += dyv.y * xh.y; ag.z += dyv.z * xh.z; ag.w += dyv.w * xh.w;
+    ab.x += dyv.x; ab.y += dyv.y; ab.z += dyv.z; ab.w += dyv.w;
+  }
+  atomicAdd(dgamma + cg * 4 + 0, ag.x); atomicAdd(dgamma + cg * 4 + 1, ag.y);
+  atomicAdd(dgamma + cg * 4 + 2, ag.z); atomicAdd(dgamma + cg * 4 + 3, ag.w);
+  atomicAdd(dbeta + cg * 4 + 0, ab.x); atomicAdd(dbeta + cg * 4 + 1, ab.y);
+  atomicAdd(dbeta + cg * 4 + 2, ab.z); atomicAdd(dbeta + cg * 4 + 3, ab.w);
 }
 
 // =========================================================================================== cast + column sums
@@ -460,6 +460,50 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restric
     }
   }
 }
+// vector path (ldx, ldy, n multiples of 4, n == ldy): thread = float4 column group, block = 64 rows x 1024 columns
+__global__ void __launch_bounds__(256) cast_colsum_vec_kernel(const float* __restrict__ x, int ldx, bf16* __restrict__ y,
+                                                              int ldy, float* __restrict__ colsum, int rows, int n,
+                                                              int rows_per_block) {
+  const int cg = blockIdx.y * 256 + threadIdx.x;
+  if (cg * 4 >= n) return;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+  for (int r = r0; r < r1; ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ldx + cg * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (y) *reinterpret_cast<uint2*>(y + static_cast<size_t>(r) * ldy + cg * 4) =
+        make_uint2(cvt_bf16x2(v.x, v.y), cvt_bf16x2(v.z, v.w));
+  }
+  if (colsum) {
+    atomicAdd(colsum + cg * 4 + 0, s.x); atomicAdd(colsum + cg * 4 + 1, s.y);
+    atomicAdd(colsum + cg * 4 + 2, s.z); atomicAdd(colsum + cg * 4 + 3, s.w);
+  }
+}
+// column sums of a bf16 matrix, 8 columns per thread (n % 8 == 0, 16-byte aligned rows)
+__global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(const bf16* __restrict__ x, int ldx,
+                                                              float* __restrict__ colsum, int rows, int n,
+                                                              int rows_per_block) {
+  const int cg = blockIdx.y * 256 + threadIdx.x;
+  if (cg * 8 >= n) return;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int r = r0; r < r1; ++r) {
+    const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * ldx + cg * 8);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[2 * i] += __uint_as_float(w[i] << 16);
+      s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(colsum + cg * 8 + i, s[i]);
+}
+
 // column sums of a bf16 matrix (bias gradient of the FFN hidden layer)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int ldx,
                                                           float* __restrict__ colsum, int rows, int n,
@@ -585,9 +629,12 @@ int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float*
   if ((rc = make_tmap_bf16(&tmy, dy_bf16, tokens, out_dim, ldy, 64, 64))) return rc;
   const int tiles_in = (in_dim + WG_BM - 1) / WG_BM, tiles_out = (out_dim + WG_BN - 1) / WG_BN;
   const int num_kb = (tokens + WG_BK - 1) / WG_BK;
-  int splits = (2 * num_sms()) / (tiles_in * tiles_out);
+  // enough (tile, K-slice) work items for >= 4 full waves (168 tiles on 148 SMs with one slice each would leave the
+  // second wave 13 % full), but at least 16 K blocks per slice so the fp32 red.add epilogue stays amortised
+  const int tiles = tiles_in * tiles_out;
+  int splits = (4 * num_sms() + tiles - 1) / tiles;
+  if (splits > num_kb / 16) splits = num_kb / 16;
   if (splits < 1) splits = 1;
-  if (splits > num_kb) splits = num_kb;
   const int kb_per = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per - 1) / kb_per;
   dim3 grid(tiles_out, tiles_in, splits);
@@ -640,25 +687,39 @@ int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* 
 }
 
 int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, float* dgamma,
-                float* dbeta, int rows, int d, cudaStream_t st) {
+                float* dbeta, float* stats, int rows, int d, cudaStream_t st) {
   FACT_REQUIRE(d % 4 == 0 && d <= 1024, FACT_ERR_BAD_SHAPE, "ln_backward: d %d", d);
-  int grid = (rows + 7) / 8;
-  if (grid > 4 * num_sms()) grid = 4 * num_sms();
-  ln_bwd_kernel<<<grid, 256, 0, st>>>(x, gamma, dy, dres, dx, dgamma, dbeta, rows, d);
-  FACT_LAUNCH_CHECK("ln_bwd_kernel");
+  FACT_REQUIRE(stats != nullptr, FACT_ERR_BAD_SHAPE, "ln_backward: stats scratch missing");
+  ln_bwd_stats_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, dy, reinterpret_cast<float4*>(stats), rows, d);
+  FACT_LAUNCH_CHECK("ln_bwd_stats_kernel");
+  ln_bwd_apply_kernel<<<(rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK, 256, 0, st>>>(
+      x, gamma, dy, dres, reinterpret_cast<const float4*>(stats), dx, dgamma, dbeta, rows, d);
+  FACT_LAUNCH_CHECK("ln_bwd_apply_kernel");
   return FACT_OK;
 }
 
 int cast_colsum(const float* x, int ldx, void* y, int ldy, float* colsum, int rows, int n, cudaStream_t st) {
   const int rpb = 64;
-  cast_colsum_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(x, ldx, static_cast<bf16*>(y), ldy, colsum, rows, n, rpb);
+  const bool vec = (n % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && n == ldy &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!y || (reinterpret_cast<uintptr_t>(y) & 7) == 0);
+  if (vec) {
+    dim3 grid((rows + rpb - 1) / rpb, (n / 4 + 255) / 256);
+    cast_colsum_vec_kernel<<<grid, 256, 0, st>>>(x, ldx, static_cast<bf16*>(y), ldy, colsum, rows, n, rpb);
+  } else {
+    cast_colsum_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(x, ldx, static_cast<bf16*>(y), ldy, colsum, rows, n, rpb);
+  }
   FACT_LAUNCH_CHECK("cast_colsum_kernel");
   return FACT_OK;
 }
 
 int colsum_bf16(const void* x, int ldx, float* colsum, int rows, int n, cudaStream_t st) {
   const int rpb = 64;
-  colsum_bf16_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(static_cast<const bf16*>(x), ldx, colsum, rows, n, rpb);
+  if (n % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    dim3 grid((rows + rpb - 1) / rpb, (n / 8 + 255) / 256);
+    colsum_bf16_vec_kernel<<<grid, 256, 0, st>>>(static_cast<const bf16*>(x), ldx, colsum, rows, n, rpb);
+  } else {
+    colsum_bf16_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(static_cast<const bf16*>(x), ldx, colsum, rows, n, rpb);
+  }
   FACT_LAUNCH_CHECK("colsum_bf16_kernel");
   return FACT_OK;
 }
@@ -714,10 +775,11 @@ extern "C" int fact_sdpa_backward(const void* qkv, const void* o, const void* d_
 }
 
 extern "C" int fact_layernorm_backward(const float* x, const float* gamma, const float* dy, const float* dres,
-                                       float* dx, float* dgamma, float* dbeta, int rows, int d, void* stream) {
-  FACT_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && rows > 0, FACT_ERR_BAD_SHAPE,
+                                       float* dx, float* dgamma, float* dbeta, float* stats_scratch, int rows, int d,
+                                       void* stream) {
+  FACT_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && stats_scratch && rows > 0, FACT_ERR_BAD_SHAPE,
                "fact_layernorm_backward: bad arguments");
-  return ln_backward(x, gamma, dy, dres, dx, dgamma, dbeta, rows, d, as_stream(stream));
+  return ln_backward(x, gamma, dy, dres, dx, dgamma, dbeta, stats_scratch, rows, d, as_stream(stream));
 }
 
 extern "C" int fact_embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dw, float* dbias,

@@ -19,7 +19,7 @@ int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float*
 int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* Dv, float* dq_acc,
                   void* dqkv, int batch, int n, int heads, int head_dim, float scale, cudaStream_t st);
 int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, float* dgamma,
-                float* dbeta, int rows, int d, cudaStream_t st);
+                float* dbeta, float* stats, int rows, int d, cudaStream_t st);
 int cast_colsum(const float* x, int ldx, void* y, int ldy, float* colsum, int rows, int n, cudaStream_t st);
 int colsum_bf16(const void* x, int ldx, float* colsum, int rows, int n, cudaStream_t st);
 int slice_rows(const float* src, float* dst, long long rows_dst, int d, int seq_dst, int seq_src, int seq_off,
@@ -49,7 +49,7 @@ struct TrainWs {
   float* partial;      // 1024
   float *dy, *dym, *dya, *dln;  // [Mc, d] fp32 (dym / dya: encoder-sized)
   bf16 *dy_b, *dz_b, *dao_b, *dqkv_b;
-  float *Dscr, *dq_scr;
+  float *Dscr, *dq_scr, *ln_stats;
 };
 
 static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
@@ -103,6 +103,7 @@ static size_t carve_train(const fact_dims* dm, int batch, void* base, TrainWs* w
   w.dqkv_b = reinterpret_cast<bf16*>(take(Mc * 3 * d * 2));
   w.Dscr = reinterpret_cast<float*>(take(static_cast<size_t>(batch) * H * seq[2] * 4));
   w.dq_scr = reinterpret_cast<float*>(take(Mc * d * 4));
+  w.ln_stats = reinterpret_cast<float*>(take(Mc * 16));
   if (ws) *ws = w;
   return off;
 }
@@ -179,7 +180,7 @@ static int layer_bwd(const fact_dims* dm, const fact_layer_weights& L, const fac
   e.out_f32 = ws.dln;
   e.ldo = d;
   if ((rc = bf16_gemm(ws.dz_b, ff, L.w1_kl, ff, M, d, ff, &e, st))) return rc;  // d ln2 = dz . W1^T
-  if ((rc = ln_backward(S.x_mid, L.ln2_gamma, ws.dln, dy, dy, G.ln2_gamma, G.ln2_beta, M, d, st))) return rc;
+  if ((rc = ln_backward(S.x_mid, L.ln2_gamma, ws.dln, dy, dy, G.ln2_gamma, G.ln2_beta, ws.ln_stats, M, d, st))) return rc;
   // ---- Residual(Norm(Attention)): dy is now dL/d x_mid
   if ((rc = cast_colsum(dy, d, ws.dy_b, d, G.bo, M, d, st))) return rc;
   if ((rc = wgrad_gemm(S.ao, d, ws.dy_b, d, G.wo, d, M, d, d, st))) return rc;
@@ -199,7 +200,7 @@ static int layer_bwd(const fact_dims* dm, const fact_layer_weights& L, const fac
   e.out_f32 = ws.dln;
   e.ldo = d;
   if ((rc = bf16_gemm(ws.dqkv_b, 3 * d, L.wqkv_kl, 3 * d, M, d, 3 * d, &e, st))) return rc;  // d ln1 = dqkv . Wqkv^T
-  return ln_backward(S.x_in, L.ln1_gamma, ws.dln, dy, dy, G.ln1_gamma, G.ln1_beta, M, d, st);
+  return ln_backward(S.x_in, L.ln1_gamma, ws.dln, dy, dy, G.ln1_gamma, G.ln1_beta, ws.ln_stats, M, d, st);
 }
 
 }  // namespace fact

@@ -9,7 +9,7 @@ SIGNATURES: dict = {
     "fact_sdpa_lse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fact_wgrad_gemm": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "fact_sdpa_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
-    "fact_layernorm_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "fact_layernorm_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "fact_embed_backward": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fact_cast_colsum": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     "fact_cast_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -122,9 +122,12 @@ def test_layernorm_backward(fact_lib, cuda, rows, d, with_res):
     dx = torch.empty(rows, d, device=cuda)
     dg = torch.zeros(d, device=cuda)
     db = torch.zeros(d, device=cuda)
+    stats = torch.zeros(rows, 4, device=cuda)
+    if with_res:
+        dx = dres.clone()          # in place on the residual gradient, as the engine uses it
     L.check(fact_lib.fact_layernorm_backward(x.data_ptr(), gamma.data_ptr(), dy.data_ptr(),
-                                             dres.data_ptr() if with_res else None, dx.data_ptr(), dg.data_ptr(),
-                                             db.data_ptr(), rows, d, _st()))
+                                             dx.data_ptr() if with_res else None, dx.data_ptr(), dg.data_ptr(),
+                                             db.data_ptr(), stats.data_ptr(), rows, d, _st()))
     xx = x.double().requires_grad_(True)
     gg = gamma.double().requires_grad_(True)
     bb = torch.zeros(d, device=cuda, dtype=torch.float64, requires_grad=True)
