@@ -10,7 +10,8 @@
 //     tcgen05.st and consumed by the PV MMA as a TMEM A-operand -- probabilities never touch shared or global memory;
 //   * Q/K/V head slices arrive by TMA as [rows][16]-element sub-tiles (SWIZZLE_32B; 80 = 5 x 16 so no padding);
 //     K sub-tiles are K-major B operands, V sub-tiles are MN-major B operands of the PV product;
-//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = softmax + output (TMEM lane quadrant = warp % 4).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = softmax + output (TMEM lane quadrant = warp % 4, two
+//     warps per quadrant split the score columns and exchange row max / sum through shared memory).
 // Keys beyond N inside the last 128-key block are other rows of the qkv buffer (or TMA zero fill): their scores are
 // never read and their probabilities are written as exact zeros.
 #include "fact_internal.h"
@@ -25,7 +26,8 @@ constexpr int TC_DH = 80;
 constexpr int TC_KS = TC_DH / 16;    // 16-wide head_dim slices
 constexpr int TC_SUB = TC_KB * 32;   // bytes of one [128 rows][16 el] sub-tile
 constexpr int TC_KV_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_SM_WARPS = 8;        // softmax / output warps: two per TMEM lane quadrant, splitting the columns
+constexpr int TC_THREADS = 64 + TC_SM_WARPS * 32;
 constexpr int TC_O_COL = TC_MAXBLK * TC_KB;  // 384
 constexpr int TC_TMEM_COLS = 512;
 
@@ -34,7 +36,8 @@ struct SdpaTcCfg {
   static constexpr int PART_BYTES = TC_KS * TC_SUB;          // 20 KB: one 128 x 80 operand part
   static constexpr int TILE_BYTES = NPART * PART_BYTES;      // Q tile or one K / V block
   static constexpr int BAR_OFF = (1 + TC_KV_STAGES) * TILE_BYTES;
-  static constexpr int SMEM_BYTES = 1024 + BAR_OFF + 256;
+  static constexpr int XCHG_OFF = BAR_OFF + 256;             // 2 x [2 halves][128 rows] floats: row max, row sum
+  static constexpr int SMEM_BYTES = 1024 + XCHG_OFF + 2 * 2 * TC_QB * 4;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
@@ -78,10 +81,10 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     mbar_init(q_empty, 1);
     for (int c = 0; c < TC_MAXBLK; ++c) {
       mbar_init(s_full(c), 1);
-      mbar_init(p_full(c), 4);
+      mbar_init(p_full(c), TC_SM_WARPS);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, TC_SM_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr_addr);
@@ -176,22 +179,28 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         umma_commit(o_full);
       }
     }
-  } else {  // ------------------------------------------------------------------------ softmax + output warps 2..5
-    const int q = warp & 3;
+  } else {  // ------------------------------------------------------------------------ softmax + output warps 2..9
+    // Two warps share each TMEM lane quadrant (rows); they split the 32-column groups of every key block by parity
+    // and exchange their partial row max / row sum through shared memory with a 64-thread named barrier.
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* xmax = reinterpret_cast<float*>(smem_gen + Cfg::XCHG_OFF);   // [2][128]
+    float* xsum = xmax + 2 * TC_QB;                                     // [2][128]
+    const int rt = q * 32 + lane;                                       // row inside the tile
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); };
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const uint32_t tph = t & 1;
       int b, h, qb;
       tile_coords(tile, b, h, qb);
-      const int row = qb * TC_QB + q * 32 + lane;
-      // ---- pass 1: row max over the valid keys (scores are already in the exp2 domain)
+      const int row = qb * TC_QB + rt;
+      // ---- pass 1: row max over this warp's column groups (scores are already in the exp2 domain)
       float mx = -INFINITY;
       for (int c = 0; c < nblk; ++c) {
         mbar_wait(s_full(c), tph);
         tc_fence_after();
         const int nvalid = min(TC_KB, N - c * TC_KB);
-        for (int g = 0; g * 32 < nvalid; ++g) {
+        for (int g = half; g * 32 < nvalid; g += 2) {
           float v[32];
           tmem_ld_32x32(lane_base + c * TC_KB + g * 32, v);
           tmem_ld_wait();
@@ -200,11 +209,14 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < lim ? v[i] : -INFINITY);
         }
       }
+      xmax[half * TC_QB + rt] = mx;
+      pair_sync();
+      mx = fmaxf(mx, xmax[(half ^ 1) * TC_QB + rt]);
       // ---- pass 2: p = 2^(s - max); P_hi | P_lo overwrite the score columns they came from
       float lsum = 0.f;
       for (int c = 0; c < nblk; ++c) {
         const int nvalid = min(TC_KB, N - c * TC_KB);
-        for (int g = 0; g * 32 < nvalid; ++g) {
+        for (int g = half; g * 32 < nvalid; g += 2) {
           float v[32];
           const uint32_t addr = lane_base + c * TC_KB + g * 32;
           tmem_ld_32x32(addr, v);
@@ -231,24 +243,32 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(c));
       }
-      // ---- output: O / l, split, "b h n d -> b n (h d)"
+      xsum[half * TC_QB + rt] = lsum;
+      pair_sync();
+      lsum += xsum[(half ^ 1) * TC_QB + rt];
+      // ---- output: O / l, split, "b h n d -> b n (h d)"; half 0 takes columns [0, 48), half 1 [48, 80)
       const float inv = 1.f / lsum;
       mbar_wait(o_full, tph);
       tc_fence_after();
-      float ov[TC_DH];
-      tmem_ld_32x32(lane_base + TC_O_COL, ov);
-      tmem_ld_32x32(lane_base + TC_O_COL + 32, ov + 32);
-      tmem_ld_32x16(lane_base + TC_O_COL + 64, ov + 64);
+      constexpr int C0 = 48;
+      float ov[C0];
+      if (half == 0) {
+        tmem_ld_32x32(lane_base + TC_O_COL, ov);
+        tmem_ld_32x16(lane_base + TC_O_COL + 32, ov + 32);
+      } else {
+        tmem_ld_32x32(lane_base + TC_O_COL + C0, ov);
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (row < N) {
-        if (lse) lse[(static_cast<size_t>(b) * H + h) * N + row] = mx + log2f(lsum);
-        const size_t base = (static_cast<size_t>(b) * N + row) * D + h * TC_DH;
-        uint32_t hh[TC_DH / 2], ll[TC_DH / 2];
+        if (lse && half == 0) lse[(static_cast<size_t>(b) * H + h) * N + row] = mx + log2f(lsum);
+        const int ncol = half == 0 ? C0 : TC_DH - C0;
+        const size_t base = (static_cast<size_t>(b) * N + row) * D + h * TC_DH + (half == 0 ? 0 : C0);
+        uint32_t hh[C0 / 2], ll[C0 / 2];
 #pragma unroll
-        for (int i = 0; i < TC_DH / 2; ++i) {
+        for (int i = 0; i < C0 / 2; ++i) {
           const float x0 = ov[2 * i] * inv, x1 = ov[2 * i + 1] * inv;
           const uint32_t hp = cvt_bf16x2(x0, x1);
           hh[i] = hp;
@@ -256,12 +276,13 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
         uint4* ph = reinterpret_cast<uint4*>(o_hi + base);
 #pragma unroll
-        for (int i = 0; i < TC_DH / 8; ++i) ph[i] = make_uint4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
+        for (int i = 0; i < C0 / 8; ++i)
+          if (i * 8 < ncol) ph[i] = make_uint4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
         if (NPART == 2) {
           uint4* pl = reinterpret_cast<uint4*>(o_lo + base);
 #pragma unroll
-          for (int i = 0; i < TC_DH / 8; ++i)
-            pl[i] = make_uint4(ll[4 * i], ll[4 * i + 1], ll[4 * i + 2], ll[4 * i + 3]);
+          for (int i = 0; i < C0 / 8; ++i)
+            if (i * 8 < ncol) pl[i] = make_uint4(ll[4 * i], ll[4 * i + 1], ll[4 * i + 2], ll[4 * i + 3]);
         }
       }
     }
