@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % WG_STAGES;
-          mbar_wait(empty_bar(s), ((i / WG_STAGES) & 1) ^ 1);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        mbar_wait(empty_bar(s), ((i / WG_STAGES) & 1) ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(s), WG_STAGE_BYTES);
           const int t0 = (kb0 + i) * WG_BK;
           tma_load_2d(sA(s), &tmX, m0, t0, full_bar(s));
@@ -74,23 +74,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(
           tma_load_2d(sB(s), &tmY, n0, t0, full_bar(s));
           tma_load_2d(sB(s) + WG_BOX_BYTES, &tmY, n0 + 64, t0, full_bar(s));
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16_f32_maj(WG_BM, WG_BN, 1, 1);
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % WG_STAGES;
-          mbar_wait(full_bar(s), (i / WG_STAGES) & 1);
-          tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_bf16_f32_maj(WG_BM, WG_BN, 1, 1);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        mbar_wait(full_bar(s), (i / WG_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = umma_desc_mn_sw128(sA(s), WG_BOX_BYTES, 1024);
+          const uint64_t b0 = umma_desc_mn_sw128(sB(s), WG_BOX_BYTES, 1024);
 #pragma unroll
           for (int kk = 0; kk < WG_BK / 16; ++kk) {  // 16 tokens = two 8-row groups = 2048 bytes
-            const uint64_t a = umma_desc_mn_sw128(sA(s) + kk * 2048, WG_BOX_BYTES, 1024);
-            const uint64_t b = umma_desc_mn_sw128(sB(s) + kk * 2048, WG_BOX_BYTES, 1024);
-            umma_bf16(tmem_base, a, b, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            const uint64_t off = static_cast<uint64_t>(kk * 2048) >> 4;
+            umma_bf16(tmem_base, a0 + off, b0 + off, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
+          if (i == nkb - 1) umma_commit(done_bar);
         }
-        umma_commit(done_bar);
+        __syncwarp();
       }
     } else {
       const int q = warp & 3;

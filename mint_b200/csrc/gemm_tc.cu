@@ -156,26 +156,32 @@ __device__ __forceinline__ void epilogue_chunk(const float* v, const float4* rv,
         const float z = __uint_as_float((c & 1) ? (raw & 0xffff0000u) : (raw << 16));
         x[c] = v[c] * gelu_tanh_grad(z);
       }
+    } else if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
+      if (fast) {  // bias as 8 x 16-byte loads (warp-uniform addresses), not 32 scalar ones
+        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          x[4 * i + 0] = gelu_tanh(v[4 * i + 0] + b.x);
+          x[4 * i + 1] = gelu_tanh(v[4 * i + 1] + b.y);
+          x[4 * i + 2] = gelu_tanh(v[4 * i + 2] + b.z);
+          x[4 * i + 3] = gelu_tanh(v[4 * i + 3] + b.w);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = gelu_tanh(v[c] + (col0 + c < N ? __ldg(ep.bias + col0 + c) : 0.f));
+      }
     } else {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
-          const float b = (fast || col0 + c < N) ? __ldg(ep.bias + col0 + c) : 0.f;
-          x[c] = gelu_tanh(v[c] + b);
-        } else {
-          x[c] = (col0 + c < ep.scale_cols) ? v[c] * ep.scale : v[c];
-        }
-      }
+      for (int c = 0; c < 32; ++c) x[c] = (col0 + c < ep.scale_cols) ? v[c] * ep.scale : v[c];
     }
     if (fast) {
       uint32_t h[16], l[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        bf16 h0, l0, h1, l1;
-        split_bf16(x[2 * c], h0, l0);
-        split_bf16(x[2 * c + 1], h1, l1);
-        h[c] = pack_bf16x2(h0, h1);
-        l[c] = pack_bf16x2(l0, l1);
+      for (int c = 0; c < 16; ++c) {  // packed conversions: one cvt per pair for hi, one for lo
+        const uint32_t hp = cvt_bf16x2(x[2 * c], x[2 * c + 1]);
+        h[c] = hp;
+        l[c] = cvt_bf16x2(x[2 * c] - __uint_as_float(hp << 16), x[2 * c + 1] - __uint_as_float(hp & 0xffff0000u));
       }
       uint4* ph = reinterpret_cast<uint4*>(ep.out_hi + o);
 #pragma unroll
@@ -252,14 +258,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
   };
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
+    // ---------------- TMA producer: whole warp walks the ring, one elected lane issues
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           tma_load_2d(sA(s, 0), &tmA0, kb * BK, m0, full_bar(s));
           tma_load_2d(sB(s, 0), &tmB0, kb * BK, n0, full_bar(s));
@@ -268,38 +275,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
             tma_load_2d(sB(s, 1), &tmB1, kb * BK, n0, full_bar(s));
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // epilogue has drained this accumulator
+    // ---------------- MMA issuer: the whole warp walks the pipeline, one elected lane issues
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    uint32_t it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
+        if (elect_one()) {
+          // descriptors differ only in the start-address field: build once per stage, bump by 32 B per K step
+          const uint64_t a_hi0 = umma_desc_k_sw128(sA(s, 0)), b_hi0 = umma_desc_k_sw128(sB(s, 0));
+          const uint64_t a_lo0 = umma_desc_k_sw128(sA(s, NPART - 1)), b_lo0 = umma_desc_k_sw128(sB(s, NPART - 1));
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            const uint32_t koff = kk * UMMA_K * 2;  // bytes inside the 128-B swizzle span
-            const uint64_t a_hi = umma_desc_k_sw128(sA(s, 0) + koff);
-            const uint64_t b_hi = umma_desc_k_sw128(sB(s, 0) + koff);
-            umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            const uint64_t koff = static_cast<uint64_t>(kk * UMMA_K * 2) >> 4;
+            umma_bf16(tmem_d, a_hi0 + koff, b_hi0 + koff, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
             if (NPART == 2) {
-              const uint64_t a_lo = umma_desc_k_sw128(sA(s, 1) + koff);
-              const uint64_t b_lo = umma_desc_k_sw128(sB(s, 1) + koff);
-              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
-              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+              umma_bf16(tmem_d, a_lo0 + koff, b_hi0 + koff, idesc, 1u);
+              umma_bf16(tmem_d, a_hi0 + koff, b_lo0 + koff, idesc, 1u);
             }
           }
           umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));
         }
-        umma_commit(tmem_full_bar(acc));
+        __syncwarp();
       }
     }
   } else {  // ---------------- epilogue warps 2..9 ; TMEM lane quadrant = warp % 4, chunk parity = (warp - 2) / 4
@@ -430,15 +439,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   };
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer (both CTAs)
-      uint32_t it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / tiles_n) * (2 * BM) + rank * BM;
-        const int n0 = (tile % tiles_n) * BN + rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
+    // ---------------- TMA producer (both CTAs): whole warp walks the ring, one elected lane issues
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / tiles_n) * (2 * BM) + rank * BM;
+      const int n0 = (tile % tiles_n) * BN + rank * (BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
           else mbar_arrive_leader(full_bar(s));
           tma_load_2d_2sm(sA(s, 0), &tmA0, kb * BK, m0, full_bar(s));
@@ -448,10 +458,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
             tma_load_2d_2sm(sB(s, 1), &tmB1, kb * BK, n0, full_bar(s));
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {  // ---------------- MMA issuer (leader CTA only)
+    if (leader) {  // ---------------- MMA issuer (leader CTA only): whole warp walks, one elected lane issues
       constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
       uint32_t it = 0, t = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
@@ -464,22 +475,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_hi0 = umma_desc_k_sw128(sA(s, 0)), b_hi0 = umma_desc_k_sw128(sB(s, 0));
+            const uint64_t a_lo0 = umma_desc_k_sw128(sA(s, NPART - 1)), b_lo0 = umma_desc_k_sw128(sB(s, NPART - 1));
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            const uint32_t koff = kk * UMMA_K * 2;
-            const uint64_t a_hi = umma_desc_k_sw128(sA(s, 0) + koff);
-            const uint64_t b_hi = umma_desc_k_sw128(sB(s, 0) + koff);
-            umma_bf16_2sm(tmem_d, a_hi, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-            if (NPART == 2) {
-              const uint64_t a_lo = umma_desc_k_sw128(sA(s, 1) + koff);
-              const uint64_t b_lo = umma_desc_k_sw128(sB(s, 1) + koff);
-              umma_bf16_2sm(tmem_d, a_lo, b_hi, idesc, 1u);
-              umma_bf16_2sm(tmem_d, a_hi, b_lo, idesc, 1u);
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              const uint64_t koff = static_cast<uint64_t>(kk * UMMA_K * 2) >> 4;
+              umma_bf16_2sm(tmem_d, a_hi0 + koff, b_hi0 + koff, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              if (NPART == 2) {
+                umma_bf16_2sm(tmem_d, a_lo0 + koff, b_hi0 + koff, idesc, 1u);
+                umma_bf16_2sm(tmem_d, a_hi0 + koff, b_lo0 + koff, idesc, 1u);
+              }
             }
+            umma_commit_2sm(empty_bar(s), 0x3);  // both CTAs' stage s is free
+            if (kb == num_kb - 1) umma_commit_2sm(tmem_full_bar(acc), 0x3);
           }
-          umma_commit_2sm(empty_bar(s), 0x3);  // both CTAs' stage s is free
+          __syncwarp();
         }
-        umma_commit_2sm(tmem_full_bar(acc), 0x3);
       }
     }
   } else {  // ---------------- epilogue warps (both CTAs): this CTA's 128 rows of the pair tile

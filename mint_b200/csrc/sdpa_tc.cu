@@ -101,14 +101,18 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   };
 
   if (warp == 0) {
-    if (lane == 0) {  // ------------------------------------------------------------ TMA producer
+    {  // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
       uint32_t it = 0, t = 0;
       auto load_block = [&](uint32_t dst, uint32_t bar, int col, int row) {
-        mbar_arrive_expect_tx(bar, Cfg::TILE_BYTES);
-        for (int ks = 0; ks < TC_KS; ++ks) {
-          tma_load_2d(dst + ks * TC_SUB, &tm_hi, col + ks * 16, row, bar);
-          if (NPART == 2) tma_load_2d(dst + Cfg::PART_BYTES + ks * TC_SUB, &tm_lo, col + ks * 16, row, bar);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, Cfg::TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TC_KS; ++ks) {
+            tma_load_2d(dst + ks * TC_SUB, &tm_hi, col + ks * 16, row, bar);
+            if (NPART == 2) tma_load_2d(dst + Cfg::PART_BYTES + ks * TC_SUB, &tm_lo, col + ks * 16, row, bar);
+          }
         }
+        __syncwarp();
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         int b, h, qb;
@@ -125,7 +129,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ------------------------------------------------------------ MMA issuer
+    {  // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32_ex(TC_QB, TC_KB, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16_f32_ex(TC_QB, TC_DH, 1);
       uint32_t it = 0, t = 0;
@@ -139,22 +143,25 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           mbar_wait(kv_full(s), (it / TC_KV_STAGES) & 1);
           tc_fence_after();
           const uint32_t d = tmem_base + c * TC_KB;
+          if (elect_one()) {
+            const uint64_t qh0 = umma_desc_k_sw32(q_smem), kh0 = umma_desc_k_sw32(kv_smem(s));
+            const uint64_t ql0 = umma_desc_k_sw32(q_smem + (NPART - 1) * Cfg::PART_BYTES);
+            const uint64_t kl0 = umma_desc_k_sw32(kv_smem(s) + (NPART - 1) * Cfg::PART_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < TC_KS; ++ks) {
-            const uint64_t qh = umma_desc_k_sw32(q_smem + ks * TC_SUB);
-            const uint64_t kh = umma_desc_k_sw32(kv_smem(s) + ks * TC_SUB);
-            umma_bf16(d, qh, kh, idesc_s, ks > 0 ? 1u : 0u);
-            if (NPART == 2) {
-              const uint64_t ql = umma_desc_k_sw32(q_smem + Cfg::PART_BYTES + ks * TC_SUB);
-              const uint64_t kl = umma_desc_k_sw32(kv_smem(s) + Cfg::PART_BYTES + ks * TC_SUB);
-              umma_bf16(d, ql, kh, idesc_s, 1u);
-              umma_bf16(d, qh, kl, idesc_s, 1u);
+            for (int ks = 0; ks < TC_KS; ++ks) {
+              const uint64_t off = static_cast<uint64_t>(ks * TC_SUB) >> 4;
+              umma_bf16(d, qh0 + off, kh0 + off, idesc_s, ks > 0 ? 1u : 0u);
+              if (NPART == 2) {
+                umma_bf16(d, ql0 + off, kh0 + off, idesc_s, 1u);
+                umma_bf16(d, qh0 + off, kl0 + off, idesc_s, 1u);
+              }
             }
+            umma_commit(kv_empty(s));
+            umma_commit(s_full(c));
+            if (c == nblk - 1) umma_commit(q_empty);  // Q tile reusable once every score MMA has read it
           }
-          umma_commit(kv_empty(s));
-          umma_commit(s_full(c));
+          __syncwarp();
         }
-        umma_commit(q_empty);  // Q tile reusable once every score MMA has read it
         // ---- O = sum_c P_c . V_c   (P from TMEM, V MN-major from shared)
         for (int c = 0; c < nblk; ++c, ++it) {
           const int s = it % TC_KV_STAGES;
@@ -164,19 +171,26 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           tc_fence_after();
           const int nvalid = min(TC_KB, N - c * TC_KB);
           const int ksteps = (nvalid + 15) >> 4;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint32_t a_hi = tmem_base + c * TC_KB + 32 * (j >> 1) + 8 * (j & 1);
-            const uint64_t vh = umma_desc_mn_sw32(kv_smem(s) + j * 512, TC_SUB, 256);
-            umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vh, idesc_o, (c > 0 || j > 0) ? 1u : 0u);
-            if (NPART == 2) {
-              const uint64_t vl = umma_desc_mn_sw32(kv_smem(s) + Cfg::PART_BYTES + j * 512, TC_SUB, 256);
-              umma_bf16_ts(tmem_base + TC_O_COL, a_hi + 16, vh, idesc_o, 1u);
-              umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vl, idesc_o, 1u);
+          if (elect_one()) {
+            const uint64_t vh0 = umma_desc_mn_sw32(kv_smem(s), TC_SUB, 256);
+            const uint64_t vl0 = umma_desc_mn_sw32(kv_smem(s) + (NPART - 1) * Cfg::PART_BYTES, TC_SUB, 256);
+#pragma unroll
+            for (int j = 0; j < TC_KB / 16; ++j) {
+              if (j < ksteps) {
+                const uint32_t a_hi = tmem_base + c * TC_KB + 32 * (j >> 1) + 8 * (j & 1);
+                const uint64_t off = static_cast<uint64_t>(j * 512) >> 4;
+                umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vh0 + off, idesc_o, (c > 0 || j > 0) ? 1u : 0u);
+                if (NPART == 2) {
+                  umma_bf16_ts(tmem_base + TC_O_COL, a_hi + 16, vh0 + off, idesc_o, 1u);
+                  umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vl0 + off, idesc_o, 1u);
+                }
+              }
             }
+            umma_commit(kv_empty(s));
+            if (c == nblk - 1) umma_commit(o_full);
           }
-          umma_commit(kv_empty(s));
+          __syncwarp();
         }
-        umma_commit(o_full);
       }
     }
   } else {  // ------------------------------------------------------------------------ softmax + output warps 2..9
