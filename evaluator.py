@@ -14,7 +14,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from mint_b200 import config_util, model_builder, parallel
+import glob
+
+from mint_b200 import config_util, inputs, model_builder, parallel
 from mint_b200.evaluator import SingleTaskEvaluator
 
 
@@ -44,6 +46,17 @@ def main():
         model.flat_parameters.copy_(sd["flat_parameters"])
         model.repack()
     d = model.dims
+    if glob.glob(cfg["eval_dataset"].data_files):            # evaluator.py:50-54: the reference's TFRecords
+        clips = [b for b in inputs.create_input(cfg["eval_config"], cfg["eval_dataset"], is_training=False)]
+        mine = parallel.shard_clips(len(clips), rank, world)
+        ev = SingleTaskEvaluator((clips[i] for i in mine), model, output_dir=args.output_dir, steps=args.steps)
+        with torch.cuda.stream(torch.cuda.Stream(dev)):
+            ev.evaluate(-1)
+            torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if args.data_npz:
         data = np.load(args.data_npz)
         motion, audio = data["motion_input"], data["audio_input"]

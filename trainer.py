@@ -4,8 +4,9 @@
     python trainer.py --config_path configs/fact_v5_deeper_t10_cm12.config --model_dir /tmp/fact --steps 100
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 trainer.py ...   (sync data parallel)
 
-The reference reads AIST++ TFRecords through tf.data (not rebuilt); here the dataset is the synthetic
-generator of SURVEY.md 8d unless --data_npz points at arrays {motion_input, audio_input, target}.
+Data: the TFRecords named by train_dataset.data_files of the config (the reference's own format, read without
+TensorFlow by mint_b200/inputs.py) when that glob matches files; else --data_npz arrays {motion_input, audio_input,
+target}; else the synthetic generator of SURVEY.md 8d.
 """
 import argparse
 import json
@@ -15,7 +16,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from mint_b200 import config_util, model_builder, optim
+import glob
+
+from mint_b200 import config_util, inputs, model_builder, optim
 from mint_b200.trainer import SingleTaskTrainer
 
 
@@ -63,7 +66,13 @@ def main():
     model = model_builder.build(cfg["model"], True, device=dev, mode="bf16", seed=0)   # same init on every replica
     opt = optim.Adam(model, learning_rate=optim.learning_rate_from_config(cfg["train_config"]))
     bs = cfg["train_config"].batch_size                                     # per replica, as in the reference
-    data = npz_batches(args.data_npz, bs, rank) if args.data_npz else synthetic_batches(model.dims, bs, rank)
+    if glob.glob(cfg["train_dataset"].data_files):           # trainer.py:140-146: inputs.create_input per replica
+        data = ({k: v for k, v in b.items() if k in ("motion_input", "audio_input", "target")}
+                for b in inputs.create_input(cfg["train_config"], cfg["train_dataset"], is_training=True, seed=rank))
+    elif args.data_npz:
+        data = npz_batches(args.data_npz, bs, rank)
+    else:
+        data = synthetic_batches(model.dims, bs, rank)
     trainer = SingleTaskTrainer(data, "target", model, optimizer=opt, grad_clip_norm=args.grad_clip_norm)
     os.makedirs(args.model_dir, exist_ok=True)
     ckpts = sorted(f for f in os.listdir(args.model_dir) if f.startswith("ckpt-") and f.endswith(".pt"))
