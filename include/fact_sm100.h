@@ -157,6 +157,10 @@ typedef struct fact_gemm_epilogue {
   int seq_in, seq_out, seq_off;
   const void* aux;    /* FACT_EPI_GELU_GRAD: bf16 [m, ldaux] pre-activation saved by FACT_EPI_BIAS_GELU_SAVE */
   int ldaux;
+  /* optional fp32 scratch (16-byte aligned): lets small problems (m <= 1024) deal their K blocks over all SMs; needs
+   * splits * m * n * 4 bytes, the library uses as many splits as fit.  NULL = never split. */
+  void* splitk_scratch;
+  size_t splitk_scratch_bytes;
 } fact_gemm_epilogue;
 
 /* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).
@@ -176,7 +180,7 @@ FACT_API int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, voi
               int head_dim, void* stream);
 
 /* Developer switches (defaults in brackets): "sdpa_legacy" [0] = 1 forces the generic mma.sync attention kernel;
- * "gemm_pair" [1] = 0 forces the 1-SM GEMM, 2 forces the CTA-pair GEMM; "ar_prune" [1] = 0 runs the full last layer
+ * "gemm_pair" [1] = 0 forces the 1-SM GEMM, 2 forces the CTA-pair GEMM; "gemm_splitk" [1] = 0 disables split-K; "ar_prune" [1] = 0 runs the full last layer
  * in fact_infer_auto_regressive instead of the row-0 tail. */
 FACT_API int fact_set_flag(const char* name, int value);
 

@@ -278,21 +278,35 @@ int gemm_simt_split(const void* a_hi, const void* a_lo, int lda, const float* w_
 }
 
 // ------------------------------------------------------------------------------------------- head on one row / sample
-__global__ void __launch_bounds__(256) head_rows_kernel(const float* __restrict__ x, long long row_stride,
-                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                        float* __restrict__ out, long long out_batch_stride,
-                                                        const int* __restrict__ step_ptr, int d, int out_dim) {
-  extern __shared__ float xs[];
+__global__ void __launch_bounds__(1024) head_rows_kernel(const float* __restrict__ x, long long row_stride,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ out, long long out_batch_stride,
+                                                         const int* __restrict__ step_ptr, int d, int out_dim) {
+  // one block per clip; 4 groups of 256 threads split the reduction dimension (the serial 800-long FMA chain of a
+  // single group made this 144 us at batch 1), partials meet in shared memory
+  extern __shared__ float xs[];          // [d] input row, then [3][out_dim_pad] partials
   const int b = blockIdx.x;
+  const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
   const float* xr = x + static_cast<size_t>(b) * row_stride * d;
   for (int i = threadIdx.x; i < d; i += blockDim.x) xs[i] = xr[i];
   __syncthreads();
+  float* part = xs + d;
   const int step = step_ptr ? *step_ptr : 0;
-  for (int j = threadIdx.x; j < out_dim; j += blockDim.x) {
+  const int k0 = grp * ((d + 3) / 4), k1 = min(d, k0 + (d + 3) / 4);
+  for (int j0 = 0; j0 < out_dim; j0 += 256) {
+    const int j = j0 + t;
     float acc = 0.f;
+    if (j < out_dim) {
 #pragma unroll 8
-    for (int k = 0; k < d; ++k) acc = fmaf(xs[k], __ldg(w + static_cast<size_t>(k) * out_dim + j), acc);
-    out[static_cast<size_t>(b) * out_batch_stride + static_cast<size_t>(step) * out_dim + j] = acc + bias[j];
+      for (int k = k0; k < k1; ++k) acc = fmaf(xs[k], __ldg(w + static_cast<size_t>(k) * out_dim + j), acc);
+    }
+    if (grp > 0 && j < out_dim) part[(grp - 1) * 256 + t] = acc;
+    __syncthreads();
+    if (grp == 0 && j < out_dim) {
+      acc += part[t] + part[256 + t] + part[512 + t];
+      out[static_cast<size_t>(b) * out_batch_stride + static_cast<size_t>(step) * out_dim + j] = acc + bias[j];
+    }
+    __syncthreads();
   }
 }
 
@@ -442,8 +456,8 @@ extern "C" int fact_head_rows(const float* x, long long row_stride, const float*
                               int out_dim, void* stream) {
   FACT_REQUIRE(x && w_keras && bias && out, FACT_ERR_BAD_SHAPE, "fact_head_rows: null buffer");
   FACT_REQUIRE(batch > 0 && d > 0 && d <= 8192 && out_dim > 0, FACT_ERR_BAD_SHAPE, "fact_head_rows: bad shape");
-  head_rows_kernel<<<batch, 256, d * sizeof(float), as_stream(stream)>>>(x, row_stride, w_keras, bias, out,
-                                                                         out_batch_stride, step_ptr, d, out_dim);
+  head_rows_kernel<<<batch, 1024, (d + 3 * 256) * sizeof(float), as_stream(stream)>>>(
+      x, row_stride, w_keras, bias, out, out_batch_stride, step_ptr, d, out_dim);
   FACT_LAUNCH_CHECK("head_rows_kernel launch");
   return FACT_OK;
 }

@@ -27,6 +27,8 @@ int step_inc(int* p, cudaStream_t st);
 struct Workspace {
   float *xm, *xa, *xc, *xr;
   bf16 *ln_hi, *ln_lo, *ao_hi, *ao_lo, *qkv_hi, *qkv_lo, *h_hi, *h_lo;
+  float* splitk;        // split-K partial slabs (small-M GEMMs)
+  size_t splitk_bytes;
 };
 
 static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
@@ -55,6 +57,9 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
   w.qkv_lo = lo ? reinterpret_cast<bf16*>(take(tc * 3 * d * 2)) : nullptr;
   w.h_hi = reinterpret_cast<bf16*>(take(tc * ff * 2));
   w.h_lo = lo ? reinterpret_cast<bf16*>(take(tc * ff * 2)) : nullptr;
+  // up to 16 slabs of the widest small-M GEMM output (GEMMs with m <= 1024: batch-1/2 decode, the row-0 AR tail)
+  w.splitk_bytes = 16 * (tc < 1024 ? tc : 1024) * (3 * d > ff ? 3 * d : ff) * 4;
+  w.splitk = reinterpret_cast<float*>(take(w.splitk_bytes));
   if (ws) *ws = w;
   return off;
 }
@@ -73,7 +78,14 @@ static int check_dims(const fact_dims* dm) {
 
 // GEMM dispatch on mode
 static int dense(int mode, const bf16* a_hi, const bf16* a_lo, int lda, const void* w_hi, const void* w_lo,
-                 const float* w_f32, int m, int n, int k, const fact_gemm_epilogue* e, cudaStream_t st) {
+                 const float* w_f32, int m, int n, int k, const fact_gemm_epilogue* e_in, cudaStream_t st,
+                 const Workspace* ws = nullptr) {
+  fact_gemm_epilogue e_copy = *e_in;
+  if (ws && ws->splitk) {
+    e_copy.splitk_scratch = ws->splitk;
+    e_copy.splitk_scratch_bytes = ws->splitk_bytes;
+  }
+  const fact_gemm_epilogue* e = &e_copy;
   if (mode == FACT_MODE_FP32_SIMT) return gemm_simt_split(a_hi, a_lo, lda, w_f32, m, n, k, e, st);
   if (mode == FACT_MODE_PRECISE) {
     FACT_REQUIRE(w_lo != nullptr, FACT_ERR_BAD_SHAPE, "precise mode needs the lo half of every packed weight");
@@ -98,7 +110,7 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
   e.ldo = 3 * d;
   e.scale = static_cast<float>(1.0 / sqrt(static_cast<double>(d)) * 1.4426950408889634);  // d_model^-0.5 * log2(e)
   e.scale_cols = d;
-  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st))) return rc;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st, &ws))) return rc;
   if ((rc = fact_sdpa(ws.qkv_hi, lo ? ws.qkv_lo : nullptr, ws.ao_hi, lo ? ws.ao_lo : nullptr, batch, seq, H, dh, st)))
     return rc;
   e = fact_gemm_epilogue{};
@@ -108,7 +120,7 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
   e.bias = L.bo;
   e.resid = x;
   e.ldr = d;
-  if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, d, L.wo_hi, L.wo_lo, L.wo_f32, M, d, d, &e, st))) return rc;
+  if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, d, L.wo_hi, L.wo_lo, L.wo_f32, M, d, d, &e, st, &ws))) return rc;
   // --- Residual(Norm(MLP))
   if ((rc = fact_layernorm_split(x, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
   e = fact_gemm_epilogue{};
@@ -117,7 +129,7 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
   e.out_lo = lo ? ws.h_lo : nullptr;
   e.ldo = ff;
   e.bias = L.b1;
-  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.w1_hi, L.w1_lo, L.w1_f32, M, ff, d, &e, st))) return rc;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.w1_hi, L.w1_lo, L.w1_f32, M, ff, d, &e, st, &ws))) return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_BIAS_RESID_F32;
   e.out_f32 = dst ? dst : x;
@@ -130,7 +142,7 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
     e.seq_out = dst_seq;
     e.seq_off = dst_off;
   }
-  return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, M, d, ff, &e, st);
+  return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, M, d, ff, &e, st, &ws);
 }
 
 // Last cross-modal layer of an AR step: infer_auto_regressive keeps only output row 0 of each clip
@@ -152,7 +164,7 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
   e.ldo = 3 * d;
   e.scale = static_cast<float>(1.0 / sqrt(static_cast<double>(d)) * 1.4426950408889634);
   e.scale_cols = d;
-  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st))) return rc;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.wqkv_hi, L.wqkv_lo, L.wqkv_f32, M, 3 * d, d, &e, st, &ws))) return rc;
   if ((rc = sdpa_run(ws.qkv_hi, lo ? ws.qkv_lo : nullptr, ws.ao_hi, lo ? ws.ao_lo : nullptr, nullptr, batch, seq, H, dh, 1, st)))
     return rc;
   const int pitch = seq * d;  // row 0 of clip b lives at b * seq * d
@@ -163,7 +175,7 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
   e.bias = L.bo;
   e.resid = x;
   e.ldr = pitch;
-  if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, pitch, L.wo_hi, L.wo_lo, L.wo_f32, batch, d, d, &e, st))) return rc;
+  if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, pitch, L.wo_hi, L.wo_lo, L.wo_f32, batch, d, d, &e, st, &ws))) return rc;
   if ((rc = fact_layernorm_split(ws.xr, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, batch, d, st)))
     return rc;
   e = fact_gemm_epilogue{};
@@ -172,7 +184,7 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
   e.out_lo = lo ? ws.h_lo : nullptr;
   e.ldo = ff;
   e.bias = L.b1;
-  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.w1_hi, L.w1_lo, L.w1_f32, batch, ff, d, &e, st))) return rc;
+  if ((rc = dense(mode, ws.ln_hi, ws.ln_lo, d, L.w1_hi, L.w1_lo, L.w1_f32, batch, ff, d, &e, st, &ws))) return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_BIAS_RESID_F32;
   e.out_f32 = ws.xr;
@@ -180,7 +192,7 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
   e.bias = L.b2;
   e.resid = ws.xr;
   e.ldr = d;
-  return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, batch, d, ff, &e, st);
+  return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, batch, d, ff, &e, st, &ws);
 }
 
 static int run_stack(const fact_dims* dm, const fact_layer_weights* layers, int n_layers, float* x, int batch,

@@ -362,6 +362,151 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------- split-K (small M)
+// Batch-1 decode has M = 360 tokens: 15-45 output tiles cannot fill 148 SMs, and every CTA would pull its whole A
+// panel + W tile through one SM's TMA port.  Here the K blocks of every tile are dealt across `splits` CTAs
+// (grid = tiles x splits); each writes its fp32 partial tile to its own slab part[z][M][N] with plain 16-byte stores,
+// and gemm_finish_kernel sums the slabs and applies the fused epilogue -- no atomics, bit-reproducible.
+template <int BN, int NPART, int STAGES>
+__global__ void __launch_bounds__(192, 1) gemm_tc_splitk_kernel(
+    const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, int M, int N, int K,
+    int tiles_n, int kb_per, float* __restrict__ part) {
+  using Cfg = GemmCfg<BN, NPART, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, z = blockIdx.y;
+  const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+  const int num_kb = (K + BK - 1) / BK;
+  const int kb0 = z * kb_per, nkb = min(kb_per, num_kb - kb0);
+  constexpr int TCOLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // one accumulator
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_ptr_addr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  auto sA = [&](int s, int part_) { return smem_base + s * Cfg::STAGE_BYTES + part_ * A_TILE_BYTES; };
+  auto sB = [&](int s, int part_) {
+    return smem_base + s * Cfg::STAGE_BYTES + NPART * A_TILE_BYTES + part_ * Cfg::B_TILE_BYTES;
+  };
+  if (warp == 0) {
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        const int kc = (kb0 + i) * BK;
+        mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+        tma_load_2d(sA(s, 0), &tmA0, kc, m0, full_bar(s));
+        tma_load_2d(sB(s, 0), &tmB0, kc, n0, full_bar(s));
+        if (NPART == 2) {
+          tma_load_2d(sA(s, 1), &tmA1, kc, m0, full_bar(s));
+          tma_load_2d(sB(s, 1), &tmB1, kc, n0, full_bar(s));
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(full_bar(s), (i / STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a_hi0 = umma_desc_k_sw128(sA(s, 0)), b_hi0 = umma_desc_k_sw128(sB(s, 0));
+        const uint64_t a_lo0 = umma_desc_k_sw128(sA(s, NPART - 1)), b_lo0 = umma_desc_k_sw128(sB(s, NPART - 1));
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint64_t koff = static_cast<uint64_t>(kk * UMMA_K * 2) >> 4;
+          umma_bf16(tmem_base, a_hi0 + koff, b_hi0 + koff, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          if (NPART == 2) {
+            umma_bf16(tmem_base, a_lo0 + koff, b_hi0 + koff, idesc, 1u);
+            umma_bf16(tmem_base, a_hi0 + koff, b_lo0 + koff, idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar(s));
+        if (i == nkb - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    float* dst = part + (static_cast<size_t>(z) * M + row) * N + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (row < M) {
+        if (n0 + c0 + 32 <= N && (N & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dst + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (n0 + c0 + c < N) dst[c0 + c] = v[c];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+// acc[row, col] = sum_z part[z][row][col], then the same fused epilogues as the in-kernel path (inference kinds)
+__global__ void __launch_bounds__(256) gemm_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                                          int kind, EpiArgs ep) {
+  const long long total = static_cast<long long>(M) * N;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int row = static_cast<int>(i / N), col = static_cast<int>(i % N);
+    float x = 0.f;
+    for (int zz = 0; zz < splits; ++zz) x += part[static_cast<size_t>(zz) * total + i];
+    if (kind == FACT_EPI_SPLIT) {
+      if (col < ep.scale_cols) x *= ep.scale;
+    } else if (ep.bias) {
+      x += ep.bias[col];
+    }
+    if (kind == FACT_EPI_BIAS_GELU_SPLIT) x = gelu_tanh(x);
+    if (kind == FACT_EPI_BIAS_RESID_F32) x += ep.resid[static_cast<size_t>(row) * ep.ldr + col];
+    if (kind == FACT_EPI_SPLIT || kind == FACT_EPI_BIAS_GELU_SPLIT) {
+      bf16 h, l;
+      split_bf16(x, h, l);
+      const size_t o = static_cast<size_t>(row) * ep.ldo + col;
+      ep.out_hi[o] = h;
+      if (ep.out_lo) ep.out_lo[o] = l;
+    } else {
+      ep.out_f32[static_cast<size_t>(map_row(row, ep)) * ep.ldo + col] = x;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- CTA-pair variant
 // cta_group::2: a cluster of two CTAs (one TPC) computes a 256 x BN tile.  CTA r stages A rows [128 r, 128 r + 128)
 // and W rows [BN/2 r, BN/2 r + BN/2); the leader's single thread issues tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16)
@@ -642,6 +787,28 @@ static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   return FACT_OK;
 }
 
+template <int BN, int NPART, int STAGES>
+static int launch_splitk(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+                         int m, int n, int k, int splits, int kb_per, int kind, const EpiArgs& ep, float* part,
+                         cudaStream_t st) {
+  using Cfg = GemmCfg<BN, NPART, STAGES>;
+  auto kern = gemm_tc_splitk_kernel<BN, NPART, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles_n = (n + BN - 1) / BN, tiles_m = (m + BM - 1) / BM;
+  dim3 grid(tiles_n * tiles_m, splits);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, kb_per, part);
+  FACT_LAUNCH_CHECK("gemm_tc_splitk_kernel launch");
+  const long long total = static_cast<long long>(m) * n;
+  int fgrid = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+  gemm_finish_kernel<<<fgrid, 256, 0, st>>>(part, splits, m, n, kind, ep);
+  FACT_LAUNCH_CHECK("gemm_finish_kernel launch");
+  return FACT_OK;
+}
+
 template <int BN, int NPART, int STAGES, int EPI>
 static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                        int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
@@ -713,7 +880,8 @@ int gemm_tile_n(int n) {
   return 128;
 }
 
-int g_gemm_pair = 1;  // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
+int g_gemm_pair = 1;    // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
+int g_gemm_splitk = 1;  // fact_set_flag("gemm_splitk", 0) disables the small-M split-K path
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -783,6 +951,30 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
     b1 = b0;
   }
   cudaStream_t st = as_stream(stream);
+  // ---- small M: split-K over all SMs (per-split partial slabs + fused finish kernel)
+  if (!pair && g_gemm_splitk && epi->splitk_scratch && epi->kind <= FACT_EPI_BIAS_F32 && m <= 1024) {
+    const int tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
+    const int num_kb = (k + BK - 1) / BK;
+    // only when the tiles alone fill less than ~1/3 of the SMs (else the extra finish launch costs more than it buys)
+    int splits = tiles <= 48 ? (num_sms() + tiles - 1) / tiles : 1;   // about one wave of CTAs
+    if (splits > num_kb / 2) splits = num_kb / 2;          // at least 2 K blocks per CTA
+    const size_t slab = static_cast<size_t>(m) * n * sizeof(float);
+    if (splits > 1 && static_cast<size_t>(splits) * slab > epi->splitk_scratch_bytes)
+      splits = static_cast<int>(epi->splitk_scratch_bytes / slab);
+    if (splits > 1) {
+      const int kb_per = (num_kb + splits - 1) / splits;
+      splits = (num_kb + kb_per - 1) / kb_per;
+      float* part = static_cast<float*>(epi->splitk_scratch);
+      if (precise) {
+        if (bn == 160) return launch_splitk<160, 2, 3>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
+        if (bn == 256) return launch_splitk<256, 2, 2>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
+        return launch_splitk<128, 2, 3>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
+      }
+      if (bn == 160) return launch_splitk<160, 1, 6>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
+      if (bn == 256) return launch_splitk<256, 1, 4>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
+      return launch_splitk<128, 1, 6>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
+    }
+  }
   if (pair) {
     if (precise) {
       if (bn == 160) return launch_epi2<160, 2, 4>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);

@@ -51,7 +51,7 @@ def test_pack_weight(fact_lib, cuda, k, n):
     assert torch.equal(hi, rh) and torch.equal(lo, rl)
 
 
-def _gemm_case(fact_lib, cuda, m, n, k, kind, precise, seed=0, remap=None):
+def _gemm_case(fact_lib, cuda, m, n, k, kind, precise, seed=0, remap=None, splitk=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
     a = torch.randn(m, k, generator=g).to(cuda)
     w = (torch.randn(k, n, generator=g) * (1.0 / math.sqrt(k))).to(cuda)     # Keras layout
@@ -83,6 +83,9 @@ def _gemm_case(fact_lib, cuda, m, n, k, kind, precise, seed=0, remap=None):
         e.out_f32, e.ldo = out.data_ptr(), n
         e.bias = bias.data_ptr()
         e.resid, e.ldr = resid.data_ptr(), n
+    if splitk:
+        scratch = torch.full((8 * m * n,), float("nan"), device=cuda)
+        e.splitk_scratch, e.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
     L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, k, w_hi.data_ptr(),
                                w_lo.data_ptr() if precise else None, k, m, n, k, C.byref(e), _st()), "fact_gemm")
     torch.cuda.synchronize()
@@ -155,6 +158,20 @@ def test_gemm_pair_vs_single_bitwise(fact_lib, cuda):
         outs.append((o_hi.clone(), o_lo.clone()))
     fact_lib.fact_set_flag(b"gemm_pair", 1)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32])
+@pytest.mark.parametrize("m,n,k", [(360, 2400, 800), (360, 800, 3072), (360, 3072, 800), (120, 800, 800),
+                                   (128, 226, 800), (77, 128, 200)])
+def test_gemm_tc_splitk(fact_lib, cuda, m, n, k, kind, precise):
+    """Small-M path: K blocks dealt over the SMs, per-split slabs reduced by the finish kernel (scratch pre-filled with
+    NaN: every slab element that is read must have been written)."""
+    _gemm_case(fact_lib, cuda, m, n, k, kind, precise, seed=11, splitk=True)
+
+
+def test_gemm_tc_splitk_remap_and_pitch(fact_lib, cuda):
+    _gemm_case(fact_lib, cuda, 2 * 120, 800, 3072, L.EPI_BIAS_RESID_F32, True, remap=(120, 360, 0), splitk=True)
 
 
 def test_gemm_tc_remap(fact_lib, cuda):
