@@ -171,3 +171,43 @@ def test_input_validation(cuda, fact_lib):
         m({"motion_input": torch.zeros(1, 11, 225), "audio_input": torch.zeros(1, 20, 35)})
     with pytest.raises(ValueError):
         m.infer_auto_regressive({"motion_input": torch.zeros(1, 12, 225), "audio_input": torch.zeros(1, 19, 35)})
+
+
+def test_full_size_batch_invariance_and_determinism(cuda, fact_lib):
+    """Size-independent properties at the BASELINE batch (128 clips, fact_v5): clips are independent, so (i) a clip's
+    output does not depend on its position in the batch or on its neighbours (bitwise: every tile sees the same K
+    order), (ii) two runs are bitwise identical, (iii) the batch-128 result equals the batch-2 result of the same
+    clips up to fp32 summation order (different kernels: CTA-pair vs 1-SM / split-K)."""
+    dims = oracle_dims()
+    w = O.init_weights(dims, seed=0)
+    m = _model(make_config(), w, "precise")
+    two = O.synthetic_inputs(dims, batch=2, seed=9)
+    motion = torch.from_numpy(two["motion_input"]).float()
+    audio = torch.from_numpy(two["audio_input"]).float()
+    idx = torch.arange(128) % 2
+    idx[5], idx[6] = 1, 0                                    # break the regular pattern
+    big = {"motion_input": motion[idx], "audio_input": audio[idx]}
+    out = m(big)
+    assert torch.isfinite(out).all()
+    ref0, ref1 = out[0], out[1]
+    for b in range(128):
+        assert torch.equal(out[b], ref0 if idx[b] == 0 else ref1), b
+    assert torch.equal(m(big), out)
+    small = m({"motion_input": motion, "audio_input": audio})
+    assert (small - out[:2]).abs().max() <= 3e-5 * out[:2].abs().max()
+
+
+def test_full_size_ar_frames_feed_back(cuda, fact_lib):
+    """Batch 128, 3 frames: frame i is row 0 of a plain forward on the window shifted by i (fact_model.py:123-131)."""
+    dims = oracle_dims()
+    m = FACTModel(make_config(), is_training=False, mode="precise", seed=3)
+    g = torch.Generator().manual_seed(4)
+    motion = 0.5 * torch.randn(128, 120, 225, generator=g)
+    audio = torch.randn(128, 242, 35, generator=g)
+    frames = m.infer_auto_regressive({"motion_input": motion, "audio_input": audio}, steps=3)
+    assert tuple(frames.shape) == (128, 3, 225)
+    win = motion.cuda()
+    for i in range(3):
+        row0 = m({"motion_input": win, "audio_input": audio[:, i:i + 240]})[:, :1]
+        assert (row0[:, 0] - frames[:, i]).abs().max() <= 3e-5 * frames.abs().max()
+        win = torch.cat([win[:, 1:], frames[:, i:i + 1]], 1)
