@@ -1,12 +1,17 @@
 """CPU oracle for the FACT hot path -- TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (google-research/mint) ships no numeric golden vector for this path
-(its tests assert shapes only: mint/core/fact_model_test.py:23-54, base_models_test.py:20-40) and
-TensorFlow is not installable in this image, so this restatement cannot be checked against outputs of
-the reference itself.  It is pinned instead by (i) the reference's own shape tests, (ii) an independent
-second restatement (`fact_oracle_torch.py`, fp32 torch-CPU, written against the same file:line list) that
-must agree with this one, and (iii) structural self-checks (einops column order, softmax rows, the
-800**-0.5 scale, AR invariants) in tests/test_oracle.py.
+PARITY PIN: the reference ships no numeric golden vector for this path (its tests assert shapes only:
+mint/core/fact_model_test.py:23-54, base_models_test.py:20-40) and TensorFlow is not installable in this image, so
+real-TF outputs cannot be produced.  What IS pinned: tests/golden/fact_reference_code_small.npz holds outputs of the
+reference's OWN model code -- /root/reference/mint/core/{fact_model,base_models,base_model_util,model_builder}.py
+imported in the build container with `tensorflow` resolving to oracle/tf_shim (NumPy semantics of the ~12 TF/Keras
+primitives those files call) -- for FACTModel.call, .infer_auto_regressive (incl. the early stop) and .loss; this
+restatement reproduces them to 1e-11 in float64 (tests/test_oracle.py).  So the COMPOSITION (layer order, einsum and
+Rearrange patterns, the dim**-0.5 scale, concat order, residual wiring, kept row, shift) is pinned to the reference's
+code; the primitives (Dense = x@W+b, LayerNormalization eps-inside-sqrt biased variance, softmax, tanh) carry their
+documented Keras semantics and remain UNPINNED against real TensorFlow numerics.  Further checks: an independent
+second restatement (`fact_oracle_torch.py`), the reference's own shape tests, and structural self-checks
+(tests/test_oracle.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
 package; the product (mint_b200/) never does and fails loudly without its CUDA library.

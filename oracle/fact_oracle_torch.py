@@ -1,6 +1,7 @@
 """Second, independent CPU restatement of the FACT hot path in torch (fp32 by default) -- TEST INFRASTRUCTURE.
 
-PARITY UNPINNED (see fact_oracle.py).  Written separately from the NumPy oracle, against the same reference
+Parity pin: see fact_oracle.py (pinned to the reference's own model code run over a NumPy shim of TF; real-TF
+numerics unpinned).  Written separately from the NumPy oracle, against the same reference
 lines, so the two can cross-check each other; it is also the "port" CPU baseline that bench.py times (the
 reference's TF-CPU path cannot run: TensorFlow is absent from the image) and, being differentiable, the
 autograd ground truth for the backward kernels.

@@ -211,3 +211,25 @@ def test_full_size_ar_frames_feed_back(cuda, fact_lib):
         row0 = m({"motion_input": win, "audio_input": audio[:, i:i + 240]})[:, :1]
         assert (row0[:, 0] - frames[:, i]).abs().max() <= 3e-5 * frames.abs().max()
         win = torch.cat([win[:, 1:], frames[:, i:i + 1]], 1)
+
+
+def test_cuda_path_matches_the_references_own_model_code(cuda, fact_lib):
+    """CUDA (C ABI) vs golden vectors produced by the reference's FACTModel code itself (NumPy shim of TF, float64):
+    call, infer_auto_regressive with the early stop, loss."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fact_reference_code_small.npz"))
+    meta = json.loads(str(g["meta"]))
+    cfg = make_config(d=meta["d"], heads=meta["heads"], ff=meta["ff"], layers=tuple(meta["layers"]),
+                      motion_seq=meta["motion_seq"], audio_seq=meta["audio_seq"])
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w:")}
+    for mode, tol in (("precise", 2e-4), ("fp32_simt", 2e-4)):
+        m = _model(cfg, w, mode)
+        motion, audio = torch.from_numpy(g["motion"]), torch.from_numpy(g["audio"])
+        out = m({"motion_input": motion, "audio_input": audio[:, :meta["audio_seq"]]}).cpu().numpy()
+        scale = max(1.0, np.abs(g["call"]).max())
+        assert np.abs(out - g["call"]).max() <= tol * scale, (mode, np.abs(out - g["call"]).max())
+        ar = m.infer_auto_regressive({"motion_input": motion, "audio_input": audio}, steps=meta["steps"]).cpu().numpy()
+        assert ar.shape == g["ar"].shape and np.abs(ar - g["ar"]).max() <= tol * scale
+        loss = float(m.loss(torch.from_numpy(g["target"]), torch.from_numpy(g["call"]).float()))
+        assert abs(loss - float(g["loss"])) <= 1e-5 * float(g["loss"])

@@ -139,3 +139,30 @@ def test_committed_golden_vectors():
                                         "audio_input": inp["audio_input"][:, :dims.audio_seq]}), g["call"], atol=1e-12)
     assert np.allclose(O.infer_auto_regressive(w, dims, inp, steps=meta["steps"]), g["ar"], atol=1e-12)
     assert np.isclose(O.loss(inp["target"], g["call"]), float(g["loss"]))
+
+
+def _load_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "fact_reference_code_small.npz"))
+    meta = json.loads(str(g["meta"]))
+    dims = O.Dims(meta["d"], meta["heads"], meta["ff"], *meta["layers"], meta["motion_seq"], meta["audio_seq"],
+                  meta["motion_dim"], meta["audio_dim"], meta["out_dim"])
+    w = {k[2:]: g[k].astype(np.float64) for k in g.files if k.startswith("w:")}
+    return g, meta, dims, w
+
+
+def test_oracle_matches_the_references_own_model_code():
+    """tests/golden/fact_reference_code_small.npz was produced by /root/reference's FACTModel (call,
+    infer_auto_regressive, loss) executed over a NumPy shim of the TF primitives (make_reference_golden.py): the
+    restatement must reproduce the reference code's composition exactly (float64 both sides)."""
+    g, meta, dims, w = _load_reference_golden()
+    assert set(w) == set(O.weight_shapes(dims)) and all(w[k].shape == s for k, s in O.weight_shapes(dims).items())
+    motion, audio = g["motion"].astype(np.float64), g["audio"].astype(np.float64)
+    call = O.call(w, dims, {"motion_input": motion, "audio_input": audio[:, :dims.audio_seq]})
+    assert np.abs(call - g["call"]).max() < 1e-11
+    ar = O.infer_auto_regressive(w, dims, {"motion_input": motion, "audio_input": audio}, steps=meta["steps"])
+    assert ar.shape == g["ar"].shape == (meta["batch"], meta["audio_len"] - meta["audio_seq"] + 1, 225)
+    assert np.abs(ar - g["ar"]).max() < 1e-10
+    assert abs(O.loss(g["target"], g["call"]) - float(g["loss"])) < 1e-13
+    tcall = OT.call(OT.to_torch(w, torch.float64), dims,
+                    {"motion_input": motion, "audio_input": audio[:, :dims.audio_seq]}).numpy()
+    assert np.abs(tcall - g["call"]).max() < 1e-11
