@@ -102,6 +102,67 @@ def collect_weights(model, randomize, rng):
     return {k: np.array(v, dtype=np.float32) for k, v in out.items()}
 
 
+def assign_weights(model, weights):
+    """Inverse of collect_weights: write this repo's flat dict into the (already built) reference object tree."""
+    live = collect_weights(model, False, None)               # arrays are copies: fetch the live tensors again below
+
+    def stack(prefix, transformer):
+        blocks = transformer.net.layers
+        for i in range(len(blocks) // 2):
+            attn_norm, mlp_norm = blocks[2 * i].fn, blocks[2 * i + 1].fn
+            attn, mlp = attn_norm.fn, mlp_norm.fn
+            p = f"{prefix}/layer_{i}"
+            pairs = [(attn_norm.norm.gamma, "attn/norm/gamma"), (attn_norm.norm.beta, "attn/norm/beta"),
+                     (attn.to_qkv.kernel, "attn/to_qkv/kernel"), (attn.to_out.kernel, "attn/to_out/kernel"),
+                     (attn.to_out.bias, "attn/to_out/bias"), (mlp_norm.norm.gamma, "mlp/norm/gamma"),
+                     (mlp_norm.norm.beta, "mlp/norm/beta"), (mlp.net.layers[0].kernel, "mlp/dense_0/kernel"),
+                     (mlp.net.layers[0].bias, "mlp/dense_0/bias"), (mlp.net.layers[1].kernel, "mlp/dense_1/kernel"),
+                     (mlp.net.layers[1].bias, "mlp/dense_1/bias")]
+            for t, suf in pairs:
+                t[...] = weights[f"{p}/{suf}"]
+
+    stack("cross_modal_layer/transformer", model.cross_modal_layer.transformer_layer)
+    head = model.cross_modal_layer.cross_output_layer
+    head.kernel[...] = weights["cross_modal_layer/output/kernel"]
+    head.bias[...] = weights["cross_modal_layer/output/bias"]
+    for name in ("motion", "audio"):
+        stack(f"{name}_transformer", getattr(model, f"{name}_transformer"))
+        getattr(model, f"{name}_pos_embedding").pos_embedding[...] = weights[f"{name}_pos_embedding"]
+        lin = getattr(model, f"{name}_linear_embedding").net
+        lin.kernel[...] = weights[f"{name}_linear_embedding/kernel"]
+        lin.bias[...] = weights[f"{name}_linear_embedding/bias"]
+    assert set(live) == set(weights)
+
+
+def main_v5():
+    """Full fact_v5 dims: the reference code on THIS repo's seeded Keras-default weights (oracle.init_weights(seed 0),
+    too large to commit but reproducible) and synthetic inputs (seed 0, batch 1); only inputs' seed and the outputs are
+    stored."""
+    sys.path.insert(0, ROOT)
+    from oracle import fact_oracle as O
+    cfg = model_pb2.MultiModalModel()
+    with open("/root/reference/configs/fact_v5_deeper_t10_cm12.config") as f:
+        from mint.protos import pipeline_pb2
+        pipe = pipeline_pb2.TrainEvalPipelineConfig()
+        text_format.Merge(f.read(), pipe)
+    model = model_builder.build(pipe.multi_modal_model, is_training=True)
+    dims = O.FACT_V5
+    w = {k: v.astype(np.float32).astype(np.float64) for k, v in O.init_weights(dims, seed=0).items()}
+    inp = O.synthetic_inputs(dims, batch=1, audio_len=dims.audio_seq + 1, seed=0)
+    motion = inp["motion_input"].astype(np.float32).astype(np.float64)
+    audio = inp["audio_input"].astype(np.float32).astype(np.float64)
+    window = {"motion_input": tf.constant(motion), "audio_input": tf.constant(audio[:, :dims.audio_seq])}
+    model(window)                                             # build
+    assign_weights(model, w)
+    call = np.asarray(model(window))
+    ar = np.asarray(model.infer_auto_regressive({"motion_input": tf.constant(motion), "audio_input": tf.constant(audio)},
+                                                steps=1200))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fact_reference_code_v5.npz")
+    np.savez_compressed(path, call=call, ar=ar, meta=json.dumps({"weights_seed": 0, "inputs_seed": 0, "batch": 1,
+                                                                 "audio_len": dims.audio_seq + 1}))
+    print(path, call.shape, ar.shape, float(np.abs(call).mean()))
+
+
 def main():
     m = META
     tf.set_seed(m["seed"])
@@ -131,3 +192,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_v5()

@@ -233,3 +233,22 @@ def test_cuda_path_matches_the_references_own_model_code(cuda, fact_lib):
         assert ar.shape == g["ar"].shape and np.abs(ar - g["ar"]).max() <= tol * scale
         loss = float(m.loss(torch.from_numpy(g["target"]), torch.from_numpy(g["call"]).float()))
         assert abs(loss - float(g["loss"])) <= 1e-5 * float(g["loss"])
+
+
+def test_cuda_path_matches_reference_code_at_fact_v5_size(cuda, fact_lib):
+    """The headline parity claim against the reference's own code: fact_v5 dims, Keras-default seeded weights,
+    call + 2 AR frames, per-joint L2 <= 1e-3 (precise mode)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fact_reference_code_v5.npz"))
+    dims = oracle_dims()
+    w = {k: v.astype(np.float32) for k, v in O.init_weights(dims, seed=0).items()}
+    inp = O.synthetic_inputs(dims, batch=1, audio_len=dims.audio_seq + 1, seed=0)
+    motion = torch.from_numpy(inp["motion_input"]).float()
+    audio = torch.from_numpy(inp["audio_input"]).float()
+    m = _model(make_config(), w, "precise")
+    out = m({"motion_input": motion, "audio_input": audio[:, :dims.audio_seq]}).cpu().numpy()
+    err = O.per_joint_l2(out, g["call"])
+    ar = m.infer_auto_regressive({"motion_input": motion, "audio_input": audio}, steps=1200).cpu().numpy()
+    err_ar = O.per_joint_l2(ar, g["ar"])
+    print("vs reference code, fact_v5: call", err, "AR", err_ar)
+    assert ar.shape == (1, 2, 225) and err <= PARITY_TOL and err_ar <= PARITY_TOL

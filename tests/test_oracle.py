@@ -166,3 +166,17 @@ def test_oracle_matches_the_references_own_model_code():
     tcall = OT.call(OT.to_torch(w, torch.float64), dims,
                     {"motion_input": motion, "audio_input": audio[:, :dims.audio_seq]}).numpy()
     assert np.abs(tcall - g["call"]).max() < 1e-11
+
+
+def test_oracle_matches_reference_code_at_fact_v5_size():
+    """Same pin at the real dims: the reference code (over the shim) on oracle.init_weights(FACT_V5, seed 0) rounded to
+    fp32 and synthetic_inputs(seed 0, batch 1) -- only the outputs are stored (fact_reference_code_v5.npz)."""
+    g = np.load(os.path.join(GOLDEN, "fact_reference_code_v5.npz"))
+    dims = O.FACT_V5
+    w = {k: v.astype(np.float32).astype(np.float64) for k, v in O.init_weights(dims, seed=0).items()}
+    inp = O.synthetic_inputs(dims, batch=1, audio_len=dims.audio_seq + 1, seed=0)
+    motion = inp["motion_input"].astype(np.float32).astype(np.float64)
+    audio = inp["audio_input"].astype(np.float32).astype(np.float64)
+    call = O.call(w, dims, {"motion_input": motion, "audio_input": audio[:, :dims.audio_seq]})
+    assert np.abs(call - g["call"]).max() < 1e-9
+    assert O.per_joint_l2(call, g["call"]) < 1e-9
