@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / fast-mode legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg only")
     ap.add_argument("--kernels-only", action="store_true", help="developer aid: time the hot kernels alone and exit")
+    ap.add_argument("--flag", action="append", default=[], help="developer aid: fact_set_flag name=value")
     return ap.parse_args()
 
 
@@ -278,6 +279,11 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    if args.flag:
+        from mint_b200 import lib as _L
+        for kv in args.flag:
+            name, val = kv.split("=")
+            _L.check(_L.load().fact_set_flag(name.encode(), int(val)), "fact_set_flag")
 
     cfg = config_util.get_configs_from_pipeline_file(config_util.DEFAULT_CONFIG)
     model = model_builder.build(cfg["model"], is_training=False, device=dev, mode=args.mode, seed=rank)

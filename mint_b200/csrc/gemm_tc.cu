@@ -874,7 +874,9 @@ static int launch_epi(int kind, const CUtensorMap& a0, const CUtensorMap& a1, co
   return FACT_ERR_UNSUPPORTED;
 }
 
+int g_gemm_bn = 0;  // fact_set_flag("gemm_bn", 128 | 160 | 256): force the N tile (experiments); 0 = automatic
 int gemm_tile_n(int n) {
+  if (g_gemm_bn == 128 || g_gemm_bn == 160 || g_gemm_bn == 256) return g_gemm_bn;
   if (n % 160 == 0) return 160;  // 2400 = 15 x 160, 800 = 5 x 160
   if (n % 256 == 0) return 256;  // 3072 = 12 x 256
   return 128;

@@ -267,6 +267,7 @@ int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, 
                 int head_dim, int q_rows, cudaStream_t st);
 extern int g_gemm_pair;
 extern int g_gemm_splitk;
+extern int g_gemm_bn;
 extern int g_ar_prune;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
 
@@ -281,6 +282,10 @@ extern "C" int fact_set_flag(const char* name, int value) {
   }
   if (name && strcmp(name, "ar_prune") == 0) {
     g_ar_prune = value;
+    return FACT_OK;
+  }
+  if (name && strcmp(name, "gemm_bn") == 0) {
+    g_gemm_bn = value;
     return FACT_OK;
   }
   if (name && strcmp(name, "gemm_splitk") == 0) {
