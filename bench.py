@@ -130,30 +130,55 @@ def _cpu_worker(idx, threads, steps, warmup, q):
     q.put(("done", idx, t_total))
 
 
-def cpu_frames_per_sec(steps, warmup, procs=None, threads=None):
-    """Torch-CPU fp32 restatement of the reference math on ALL host cores: `procs` independent batch-1 replicas (one
-    clip each) x `threads` intra-op threads.  A single torch process scales poorly past ~16 threads on this model
-    (67 ms / forward at 16 threads on a 128-thread Xeon 8562Y+ vs seconds at 128), so the best CPU configuration is
-    several replicas side by side -- the same clip-level parallelism the GPU arm uses.  Returns (frames/s, seconds,
-    threads_total, description)."""
-    import torch.multiprocessing as mp
+def cpu_frames_per_sec(steps, warmup, procs=1, threads=None):
+    """Torch-CPU fp32 restatement of the reference math on the host cores, batch-1 AR generation.
+
+    Measured on the GPU box (Xeon 8562Y+, 128 hardware threads): one process is fastest at 16 intra-op threads (67 ms
+    per forward = 15 frames/s); 32 / 64 / 128 threads are slower, and 8 side-by-side replicas x 16 threads drop to
+    6.9 frames/s IN TOTAL (memory-bound weight streaming, 0.5 GB per forward per replica).  So the baseline is ONE
+    replica with the thread count calibrated on a single forward: that is the most this port gets out of the box.
+    Returns (frames/s, seconds, threads_total, description)."""
+    import torch
+    from oracle import fact_oracle as O, fact_oracle_torch as OT
     ncpu = os.cpu_count() or 1
-    threads = threads or min(16, ncpu)
-    procs = procs or max(1, ncpu // threads)
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    ps = [ctx.Process(target=_cpu_worker, args=(i, threads, steps, warmup, q)) for i in range(procs)]
-    for p in ps:
-        p.start()
-    times = []
-    for _ in range(2 * procs):
-        msg = q.get(timeout=900)
-        if msg[0] == "done":
-            times.append(msg[2])
-    for p in ps:
-        p.join(60)
+    if threads is None:
+        dims = O.FACT_V5
+        w = OT.to_torch(O.init_weights(dims, seed=0))
+        one = {k: torch.from_numpy(v).float() for k, v in O.synthetic_inputs(dims, 1, seed=1).items()}
+        best = (float("inf"), min(16, ncpu))
+        for cand in sorted({c for c in (8, 16, 32, 64) if c <= ncpu}):
+            torch.set_num_threads(cand)
+            with torch.no_grad():
+                OT.call(w, dims, one)
+                t0 = time.perf_counter()
+                OT.call(w, dims, one)
+                dt = time.perf_counter() - t0
+            if dt < best[0]:
+                best = (dt, cand)
+        threads = best[1]
+        del w
+    if procs == 1:
+        import queue
+        q = queue.Queue()
+        _cpu_worker(0, threads, steps, warmup, q)
+        times = [m[2] for m in list(q.queue) if m[0] == "done"]
+    else:
+        import torch.multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        ps = [ctx.Process(target=_cpu_worker, args=(i, threads, steps, warmup, q)) for i in range(procs)]
+        for p in ps:
+            p.start()
+        times = []
+        for _ in range(2 * procs):
+            msg = q.get(timeout=900)
+            if msg[0] == "done":
+                times.append(msg[2])
+        for p in ps:
+            p.join(60)
     slowest = max(times)
-    desc = f"{procs} replicas x {threads} threads, batch 1 each, {steps} AR frames after {warmup} warm-up"
+    desc = (f"{procs} replica(s) x {threads} threads (calibrated; more threads or more replicas are slower on this "
+            f"host), batch 1, {steps} AR frames after {warmup} warm-up")
     return procs * steps / slowest, slowest, procs * threads, desc
 
 
