@@ -329,6 +329,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
 #pragma unroll
         for (int i = 0; i < 8; ++i) rv[i] = reinterpret_cast<const float4*>(rrow + n0 + half * 32)[i];
       }
+      if (EPI == FACT_EPI_BIAS_RESID_F32) {
+        // the residual tile of the NEXT tile is HBM-cold (written a layer ago): pull this thread's lines into L2 now,
+        // a whole mainloop ahead, so the epilogue loads below only pay L2 latency
+        const int nt = tile + static_cast<int>(gridDim.x);
+        if (nt < num_tiles) {
+          const int nrow = (nt / tiles_n) * BM + 0 + q * 32 + lane;
+          if (nrow < M) {
+            const float* nr = ep.resid + static_cast<size_t>(nrow) * ep.ldr + (nt % tiles_n) * BN;
+#pragma unroll
+            for (int c = half; c < BN / 32; c += 2) prefetch_l2(nr + c * 32);
+          }
+        }
+      }
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
 #pragma unroll 1
@@ -655,6 +668,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       if (EPI == FACT_EPI_BIAS_RESID_F32 && ep.vec_ok && row_ok && n0 + half * 32 + 32 <= N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) rv[i] = reinterpret_cast<const float4*>(rrow + n0 + half * 32)[i];
+      }
+      if (EPI == FACT_EPI_BIAS_RESID_F32) {
+        // the residual tile of the NEXT tile is HBM-cold (written a layer ago): pull this thread's lines into L2 now,
+        // a whole mainloop ahead, so the epilogue loads below only pay L2 latency
+        const int nt = tile + num_clusters;
+        if (nt < num_tiles) {
+          const int nrow = (nt / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + q * 32 + lane;
+          if (nrow < M) {
+            const float* nr = ep.resid + static_cast<size_t>(nrow) * ep.ldr + (nt % tiles_n) * BN;
+#pragma unroll
+            for (int c = half; c < BN / 32; c += 2) prefetch_l2(nr + c * 32);
+          }
+        }
       }
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
