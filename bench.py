@@ -380,12 +380,12 @@ def run_ours(args):
 
         extras = {}
         if rank == 0 and not args.no_extras and world == 1:
+          try:
             # BASELINE.json configs[1]: one clip (batch 1), same model / mode, device-resident
+            n1 = Wm + 4 * K
             m1 = motion_d[:1].contiguous()
-            a1 = audio_d[:1].contiguous()
-            h1 = model.new_history(m1, Wm + 4 * K)
-            model.generate_into(h1, a1[:, :dims.audio.seq_len + Wm + 4 * K - 1].contiguous(), 0, Wm)
-            a1w = a1[:, :dims.audio.seq_len + Wm + 4 * K - 1].contiguous()
+            a1w = torch.randn(1, dims.audio.seq_len + n1 - 1, dims.audio.feature_dim, device=dev)
+            h1 = model.new_history(m1, n1)
             model.generate_into(h1, a1w, 0, Wm)
             stream.synchronize()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -395,8 +395,11 @@ def run_ours(args):
             stream.synchronize()
             ms1 = f0.elapsed_time(f1) / (4 * K)
             extras["batch1"] = {"value": 1e3 / ms1, "unit": "frames/s", "ms_per_frame": ms1,
-                                "note": "configs[1]: single clip; latency-bound (116 launches per frame)"}
+                                "note": "configs[1]: single clip; latency-bound small-M launches (split-K GEMMs)"}
+          except Exception as exc:  # an extra must never cost the headline line
+            extras["batch1"] = {"error": repr(exc)[:300]}
         if rank == 0 and not args.no_extras:
+          try:
             kr = kernel_rooflines(model, B, args.mode, peaks, stream)
             extras["kernels"] = {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()}
                                  for k, v in kr.items()}
@@ -424,6 +427,8 @@ def run_ours(args):
                 "sdpa_core_gbs": kr["sdpa"]["gbs"], "sdpa_core_frac": kr["sdpa"]["gbs"] / peaks["hbm_gbs"],
                 "note": "bytes = 1600*B*N*4 + weights (SURVEY.md 8d); the block is tensor-bound (289 GFLOP/launch)",
             }
+          except Exception as exc:
+            extras["roofline"] = {"error": repr(exc)[:300]}
     fps = world * B * K / (ms * 1e-3)
     e2e_fps = world * B * K / e2e_s
 
@@ -447,12 +452,16 @@ def run_ours(args):
         }
         line.update(extras)
         if world == 1 and not args.no_extras and not args.no_cpu:
-            cpu_fps, cpu_total, threads, desc = cpu_frames_per_sec(4, 1)
-            line["cpu_baseline"] = {
-                "value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                "sample": f"{desc}; torch-CPU fp32 restatement (TensorFlow absent), {cpu_total:.1f} s"}
+            try:
+                cpu_fps, cpu_total, threads, desc = cpu_frames_per_sec(4, 1)
+                line["cpu_baseline"] = {
+                    "value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                    "sample": f"{desc}; torch-CPU fp32 restatement (TensorFlow absent), {cpu_total:.1f} s"}
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": repr(exc)[:300]}
     # throughput-mode leg (single bf16 products), reported beside the parity-grade headline
     if args.mode == "precise" and not args.no_extras and world == 1:
+      try:
         del model, hist
         torch.cuda.empty_cache()
         m2 = model_builder.build(cfg["model"], is_training=False, device=dev, mode="bf16", seed=rank)
@@ -470,6 +479,9 @@ def run_ours(args):
             line["fast_bf16"] = {"value": B * K / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / K,
                                  "note": "single bf16 products: ~4e-2 per-joint L2 vs fp64 on random-init weights; "
                                          "outside the 1e-3 parity bar, reported for throughput only"}
+      except Exception as exc:
+        if rank == 0:
+            line["fast_bf16"] = {"error": repr(exc)[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

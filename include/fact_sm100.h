@@ -180,7 +180,8 @@ FACT_API int fact_sdpa(const void* qkv_hi, const void* qkv_lo, void* out_hi, voi
               int head_dim, void* stream);
 
 /* Developer switches (defaults in brackets): "sdpa_legacy" [0] = 1 forces the generic mma.sync attention kernel;
- * "gemm_pair" [1] = 0 forces the 1-SM GEMM, 2 forces the CTA-pair GEMM; "gemm_splitk" [1] = 0 disables split-K; "ar_prune" [1] = 0 runs the full last layer
+ * "gemm_pair" [1] = 0 forces the 1-SM GEMM, 2 forces the CTA-pair GEMM; "gemm_splitk" [1] = 0 disables split-K; "dual_stream" [1] = 0 keeps both modality encoders on one stream;
+ * "gemm_bn" [0] forces the GEMM N tile (128 / 160 / 256); "ar_prune" [1] = 0 runs the full last layer
  * in fact_infer_auto_regressive instead of the row-0 tail. */
 FACT_API int fact_set_flag(const char* name, int value);
 

@@ -29,7 +29,14 @@ struct Workspace {
   bf16 *ln_hi, *ln_lo, *ao_hi, *ao_lo, *qkv_hi, *qkv_lo, *h_hi, *h_lo;
   float* splitk;        // split-K partial slabs (small-M GEMMs)
   size_t splitk_bytes;
+  // second scratch set so that the audio encoder can run concurrently with the motion encoder (small batches only)
+  bf16 *a_ln_hi, *a_ln_lo, *a_ao_hi, *a_ao_lo, *a_qkv_hi, *a_qkv_lo, *a_h_hi, *a_h_lo;
+  float* a_splitk;
+  size_t a_splitk_bytes;
 };
+
+int g_dual_stream = 1;  // fact_set_flag("dual_stream", 0): run both modality encoders on the caller's stream
+constexpr size_t kDualStreamMaxTokens = 4096;  // audio tokens (batch * 240) up to which the encoders run concurrently
 
 static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
 
@@ -60,6 +67,18 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
   // up to 16 slabs of the widest small-M GEMM output (GEMMs with m <= 1024: batch-1/2 decode, the row-0 AR tail)
   w.splitk_bytes = 16 * (tc < 1024 ? tc : 1024) * (3 * d > ff ? 3 * d : ff) * 4;
   w.splitk = reinterpret_cast<float*>(take(w.splitk_bytes));
+  if (ta <= kDualStreamMaxTokens) {
+    w.a_ln_hi = reinterpret_cast<bf16*>(take(ta * d * 2));
+    w.a_ln_lo = lo ? reinterpret_cast<bf16*>(take(ta * d * 2)) : nullptr;
+    w.a_ao_hi = reinterpret_cast<bf16*>(take(ta * d * 2));
+    w.a_ao_lo = lo ? reinterpret_cast<bf16*>(take(ta * d * 2)) : nullptr;
+    w.a_qkv_hi = reinterpret_cast<bf16*>(take(ta * 3 * d * 2));
+    w.a_qkv_lo = lo ? reinterpret_cast<bf16*>(take(ta * 3 * d * 2)) : nullptr;
+    w.a_h_hi = reinterpret_cast<bf16*>(take(ta * ff * 2));
+    w.a_h_lo = lo ? reinterpret_cast<bf16*>(take(ta * ff * 2)) : nullptr;
+    w.a_splitk_bytes = 16 * (ta < 1024 ? ta : 1024) * (3 * d > ff ? 3 * d : ff) * 4;
+    w.a_splitk = reinterpret_cast<float*>(take(w.a_splitk_bytes));
+  }
   if (ws) *ws = w;
   return off;
 }
@@ -213,18 +232,50 @@ static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* mo
   int rc;
   FACT_REQUIRE(dm->motion_layers > 0 && dm->audio_layers > 0 && dm->cross_layers > 0, FACT_ERR_UNSUPPORTED,
                "every stack needs at least one layer");
+  // The two modality encoders are independent (fact_model.py:88-96).  At small batch each is a chain of tiny,
+  // latency-bound launches, so the audio encoder runs on a second stream with its own scratch and joins before the
+  // cross-modal stack (a fork / join inside the captured graph).  At large batch the GPU is full: one stream.
+  const bool dual = g_dual_stream && ws.a_ln_hi != nullptr;
+  static thread_local cudaStream_t s2 = nullptr;
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t sa = st;
+  Workspace wa = ws;
+  if (dual) {
+    if (!s2) {
+      FACT_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      FACT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      FACT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    sa = s2;
+    wa.ln_hi = ws.a_ln_hi; wa.ln_lo = ws.a_ln_lo; wa.ao_hi = ws.a_ao_hi; wa.ao_lo = ws.a_ao_lo;
+    wa.qkv_hi = ws.a_qkv_hi; wa.qkv_lo = ws.a_qkv_lo; wa.h_hi = ws.a_h_hi; wa.h_lo = ws.a_h_lo;
+    wa.splitk = ws.a_splitk; wa.splitk_bytes = ws.a_splitk_bytes;
+    FACT_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+    FACT_CUDA_CHECK(cudaStreamWaitEvent(sa, ev_fork, 0));
+    if ((rc = fact_embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
+                         dm->audio_seq, dm->audio_dim, d, sa)))
+      return rc;
+    if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, wa, ws.xc, ns,
+                        dm->motion_seq, sa)))
+      return rc;
+    FACT_CUDA_CHECK(cudaEventRecord(ev_join, sa));
+  }
   if ((rc = fact_embed(motion, motion_bs, step_ptr, w->motion_embed_w, w->motion_embed_b, w->motion_pos, ws.xm, batch,
                        dm->motion_seq, dm->motion_dim, d, st)))
     return rc;
   if ((rc = run_stack(dm, w->motion_layers, dm->motion_layers, ws.xm, batch, dm->motion_seq, mode, ws, ws.xc, ns, 0,
                       st)))
     return rc;
-  if ((rc = fact_embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
-                       dm->audio_seq, dm->audio_dim, d, st)))
-    return rc;
-  if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, ws, ws.xc, ns,
-                      dm->motion_seq, st)))
-    return rc;
+  if (dual) {
+    FACT_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));   // join before the cross-modal stack reads xc
+  } else {
+    if ((rc = fact_embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
+                         dm->audio_seq, dm->audio_dim, d, st)))
+      return rc;
+    if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, ws, ws.xc, ns,
+                        dm->motion_seq, st)))
+      return rc;
+  }
   if (!row0_only)
     return run_stack(dm, w->cross_layers, dm->cross_layers, ws.xc, batch, ns, mode, ws, nullptr, 0, 0, st);
   if ((rc = run_stack(dm, w->cross_layers, dm->cross_layers - 1, ws.xc, batch, ns, mode, ws, nullptr, 0, 0, st)))
@@ -349,7 +400,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
            reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
            static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(hist_capacity),
            static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers + 1000 * g_ar_prune + 10000 * g_gemm_pair + 100000 * g_gemm_splitk +
-                                  1000000 * g_sdpa_legacy),
+                                  1000000 * g_sdpa_legacy + 10000000 * g_dual_stream),
            static_cast<uintptr_t>(dims->d_model)};
   cudaGraphExec_t exec = nullptr;
   {
