@@ -139,21 +139,24 @@ struct SimtArgs {
   int pos_seq;
 };
 
-// 64 x 64 tile, 16-deep K slices, 256 threads x (4 x 4) outputs.
+// TM x TN tile (64x64 or 128x128), 16-deep K slices, 256 threads x (TM/16 x TN/16) outputs each; the big tile is
+// used for the embedding projections at batch >= 8 (8x8 register blocking: 64 FMA per 16 shared loads).
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(SimtArgs p) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Ws[16][64 + 4];
+  constexpr int RM = TM / 16, RN = TN / 16;
+  __shared__ float As[16][TM + 4];
+  __shared__ float Ws[16][TN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int start = p.step_ptr ? *p.step_ptr : 0;
-  float acc[4][4];
+  float acc[RM][RN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
 
   for (int k0 = 0; k0 < p.k; k0 += 16) {
-    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    for (int e = threadIdx.x; e < TM * 16; e += 256) {
       const int r = e >> 4, kk = e & 15;  // A: k fastest -> coalesced along the row
       const int row = m0 + r, k = k0 + kk;
       float a = 0.f;
@@ -166,34 +169,35 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(SimtArgs p) {
       }
       As[kk][r] = a;
     }
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      const int kk = e >> 6, c = e & 63;
+    for (int e = threadIdx.x; e < 16 * TN; e += 256) {
+      const int kk = e / TN, c = e % TN;
       const int k = k0 + kk, col = n0 + c;
       Ws[kk][c] = (k < p.k && col < p.n) ? p.w[static_cast<size_t>(k) * p.n + col] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], w[4];
+      float a[RM], w[RN];
+      // strided ownership (row ty + 16 i, column tx + 16 j): conflict-free shared reads, coalesced global stores
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < RM; ++i) a[i] = As[kk][ty + 16 * i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+      for (int j = 0; j < RN; ++j) w[j] = Ws[kk][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int row = m0 + ty + 16 * i;
     if (row >= p.m) continue;
     const int orow = p.seq_in ? (row / p.seq_in) * p.seq_out + p.seq_off + row % p.seq_in : row;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + tx * 4 + j;
+    for (int j = 0; j < RN; ++j) {
+      const int col = n0 + tx + 16 * j;
       if (col >= p.n) continue;
       float x = acc[i][j];
       if (p.kind == FACT_EPI_SPLIT) {
@@ -224,8 +228,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(SimtArgs p) {
 }
 
 static int launch_simt(const SimtArgs& p, cudaStream_t st) {
-  dim3 grid((p.n + 63) / 64, (p.m + 63) / 64);
-  gemm_f32_kernel<<<grid, 256, 0, st>>>(p);
+  if (p.m >= 1024 && p.n >= 128) {
+    dim3 grid((p.n + 127) / 128, (p.m + 127) / 128);
+    gemm_f32_kernel<128, 128><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((p.n + 63) / 64, (p.m + 63) / 64);
+    gemm_f32_kernel<64, 64><<<grid, 256, 0, st>>>(p);
+  }
   FACT_LAUNCH_CHECK("gemm_f32_kernel launch");
   return FACT_OK;
 }

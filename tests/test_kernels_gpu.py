@@ -202,9 +202,10 @@ def test_gemm_big_tiles(fact_lib, cuda):
     _gemm_case(fact_lib, cuda, 2048, 800, 3072, L.EPI_BIAS_RESID_F32, False, seed=4)
 
 
+@pytest.mark.parametrize("m", [130, 1100])
 @pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32])
-def test_gemm_f32(fact_lib, cuda, kind):
-    m, n, k = 130, 200, 225
+def test_gemm_f32(fact_lib, cuda, kind, m):
+    n, k = 200, 225
     a = torch.randn(m, k, device=cuda)
     w = torch.randn(k, n, device=cuda) / math.sqrt(k)
     bias = torch.randn(n, device=cuda)
@@ -264,8 +265,9 @@ def _sdpa_case(fact_lib, cuda, batch, n, heads, dh, precise):
     assert (got - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), float((got - ref).abs().max())
 
 
-def test_embed_and_offsets(fact_lib, cuda):
-    batch, x_len, n_tok, f, d = 3, 50, 12, 35, 64
+@pytest.mark.parametrize("batch,n_tok,d", [(3, 12, 64), (10, 120, 800)])
+def test_embed_and_offsets(fact_lib, cuda, batch, n_tok, d):
+    x_len, f = n_tok + 38, 35
     x = torch.randn(batch, x_len, f, device=cuda)
     w = torch.randn(f, d, device=cuda)
     b = torch.randn(d, device=cuda)
