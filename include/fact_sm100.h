@@ -46,6 +46,9 @@ extern "C" {
 
 FACT_API int fact_abi_version(void);
 FACT_API const char* fact_last_error(void);
+/* Kernels launched by this library on the calling thread so far (each replay of the captured AR frame graph counts
+ * the kernels it contains). */
+FACT_API long long fact_launch_count(void);
 
 /* ---- weights -------------------------------------------------------------------------------------------- */
 

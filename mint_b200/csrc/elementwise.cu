@@ -12,6 +12,7 @@ namespace fact {
 
 // ------------------------------------------------------------------------------------------- error plumbing
 static thread_local char g_err[512] = "";
+thread_local long long g_launch_count = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -389,6 +390,7 @@ int step_inc(int* p, cudaStream_t st) {
 using namespace fact;
 
 extern "C" int fact_abi_version(void) { return FACT_ABI_VERSION; }
+extern "C" long long fact_launch_count(void) { return g_launch_count; }
 extern "C" const char* fact_last_error(void) { return g_err; }
 
 extern "C" int fact_layernorm_split(const float* x, const float* gamma, const float* beta, void* y_hi, void* y_lo,

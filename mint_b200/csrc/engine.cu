@@ -301,7 +301,11 @@ struct GraphKey {
   bool operator<(const GraphKey& o) const { return v < o.v; }
 };
 static std::mutex g_graph_mu;
-static std::map<GraphKey, cudaGraphExec_t> g_graphs;
+struct CachedGraph {
+  cudaGraphExec_t exec;
+  long long kernels;  // kernel nodes of one frame
+};
+static std::map<GraphKey, CachedGraph> g_graphs;
 
 }  // namespace fact
 
@@ -403,15 +407,22 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
                                   1000000 * g_sdpa_legacy + 10000000 * g_dual_stream),
            static_cast<uintptr_t>(dims->d_model)};
   cudaGraphExec_t exec = nullptr;
+  long long frame_kernels = 0;
   {
     std::lock_guard<std::mutex> lk(g_graph_mu);
     auto it = g_graphs.find(key);
-    if (it != g_graphs.end()) exec = it->second;
+    if (it != g_graphs.end()) {
+      exec = it->second.exec;
+      frame_kernels = it->second.kernels;
+    }
   }
   if (!exec) {
     cudaGraph_t graph = nullptr;
+    const long long before = g_launch_count;
     FACT_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = one_frame(st);
+    frame_kernels = g_launch_count - before;
+    g_launch_count = before;  // captured, not executed: replays are counted below
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc) {
       if (graph) cudaGraphDestroy(graph);
@@ -423,11 +434,12 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
     std::lock_guard<std::mutex> lk(g_graph_mu);
     if (g_graphs.size() >= 16) {  // bounded: drop everything (idle graphs only; callers sync between shapes)
-      for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second);
+      for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
       g_graphs.clear();
     }
-    g_graphs[key] = exec;
+    g_graphs[key] = CachedGraph{exec, frame_kernels};
   }
   for (int i = 0; i < n_frames; ++i) FACT_CUDA_CHECK(cudaGraphLaunch(exec, st));
+  g_launch_count += frame_kernels * n_frames;
   return FACT_OK;
 }

@@ -9,6 +9,7 @@
 
 namespace fact {
 
+extern thread_local long long g_launch_count;  // kernels launched (graph replays are added by the AR engine)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
@@ -18,8 +19,10 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::fact::cuda_fail(_e, #expr); \
   } while (0)
 
+// every kernel launch of the library passes through here: also feeds fact_launch_count()
 #define FACT_LAUNCH_CHECK(what)                                 \
   do {                                                          \
+    ++::fact::g_launch_count;                                   \
     cudaError_t _e = cudaGetLastError();                        \
     if (_e != cudaSuccess) return ::fact::cuda_fail(_e, what);  \
   } while (0)

@@ -60,6 +60,7 @@ class GemmEpilogue(C.Structure):
 SIGNATURES = {
     "fact_abi_version": (_i, []),
     "fact_last_error": (C.c_char_p, []),
+    "fact_launch_count": (C.c_longlong, []),
     "fact_pack_weight": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "fact_layernorm_split": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "fact_gemm": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp]),
