@@ -294,7 +294,7 @@ static int check_weights(const fact_dims* dm, const fact_weights* w) {
 
 // ---- graph cache for the AR loop
 int g_ar_prune = 1;  // fact_set_flag("ar_prune", 0): run the full last layer (A-B check of the row-0 pruning)
-extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy;
+extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn;
 
 struct GraphKey {
   std::vector<uintptr_t> v;
@@ -404,7 +404,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
            reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
            static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(hist_capacity),
            static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers + 1000 * g_ar_prune + 10000 * g_gemm_pair + 100000 * g_gemm_splitk +
-                                  1000000 * g_sdpa_legacy + 10000000 * g_dual_stream),
+                                  1000000 * g_sdpa_legacy + 10000000 * g_dual_stream + 100000000 * g_gemm_tma_store),
            static_cast<uintptr_t>(dims->d_model)};
   cudaGraphExec_t exec = nullptr;
   long long frame_kernels = 0;

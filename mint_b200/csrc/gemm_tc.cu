@@ -42,6 +42,7 @@ struct EpiArgs {
   int vec_ok;  // all row pitches / base pointers allow 16-byte row-chunk accesses
   const bf16* aux;  // GELU_GRAD: saved pre-activation
   int ldaux;
+  int reduce_add;  // TMA-store epilogue, BIAS_RESID_F32 with out == resid: the add is a bulk reduction in the L2
 };
 
 template <int BN, int NPART, int STAGES>
@@ -527,15 +528,18 @@ __global__ void __launch_bounds__(256) gemm_finish_kernel(const float* __restric
 // K block this stages A + W/2 instead of A + W: the measured TMA ingest limit (~64 B/cycle/SM) stops binding.
 // Barriers: full[] and tmem_empty[] are the LEADER's (peer arrives remotely, peer TMA credits the leader's barrier);
 // empty[] and tmem_full[] exist in both CTAs and are signalled by multicast tcgen05.commit.
-template <int BN, int NPART, int STAGES>
+constexpr int TS_WARP_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B (one fp32 box, or two bf16 boxes)
+template <int BN, int NPART, int STAGES, bool TS = false>
 struct Gemm2Cfg {
   static constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = NPART * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int STAGING_BYTES = TS ? EPI_WARPS * TS_WARP_BYTES : 0;
   static constexpr int ACC_COLS = 2 * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
                                    : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static_assert(STAGE_BYTES % 1024 == 0, "staging boxes need the 1024-byte alignment the stages keep");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=256 / 32-column epilogue chunks");
   static_assert((BN / 2) % 8 == 0, "W half must be whole 8-row swizzle atoms");
   static_assert(ACC_COLS <= 512, "TMEM has 512 columns");
@@ -543,23 +547,126 @@ struct Gemm2Cfg {
   static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier block too small");
 };
 
-template <int BN, int NPART, int STAGES, int EPI>
+
+// ---- TMA-store epilogue (pair kernel): the same arithmetic as epilogue_chunk, but the results stay in registers
+// (packed bf16 pairs o0/o1, or fp32 of) and the caller stages them in shared memory for one bulk tensor store per
+// 32 x 32 box.  Rows / columns outside [M, N] are computed on zeros and clipped by the store.
+__device__ __forceinline__ void load_bias32(float* b, const EpiArgs& ep, int col0, int N) {
+  if (ep.bias == nullptr) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) b[c] = 0.f;
+  } else if (ep.vec_ok && col0 + 32 <= N) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(b4 + i);
+      b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) b[c] = (col0 + c < N) ? __ldg(ep.bias + col0 + c) : 0.f;
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_compute(const float* v, int row, int col0, bool row_ok, int N,
+                                                 const EpiArgs& ep, uint32_t* o0, uint32_t* o1, float* of) {
+  if (EPI == FACT_EPI_BIAS_RESID_F32 || EPI == FACT_EPI_BIAS_F32) {
+    float b[32];
+    load_bias32(b, ep, col0, N);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) of[c] = v[c] + b[c];
+    if (EPI == FACT_EPI_BIAS_RESID_F32 && !ep.reduce_add && row_ok) {
+      const float* rrow = ep.resid + static_cast<size_t>(row) * ep.ldr + col0;
+      if (ep.vec_ok && col0 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 r = reinterpret_cast<const float4*>(rrow)[i];
+          of[4 * i] += r.x; of[4 * i + 1] += r.y; of[4 * i + 2] += r.z; of[4 * i + 3] += r.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (col0 + c < N) of[c] += rrow[c];
+      }
+    }
+    return;
+  }
+  float x[32];
+  if (EPI == FACT_EPI_BIAS_GELU_SAVE) {
+    float b[32];
+    load_bias32(b, ep, col0, N);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float z0 = v[2 * c] + b[2 * c], z1 = v[2 * c + 1] + b[2 * c + 1];
+      o1[c] = cvt_bf16x2(z0, z1);
+      o0[c] = cvt_bf16x2(gelu_tanh(z0), gelu_tanh(z1));
+    }
+    return;
+  }
+  if (EPI == FACT_EPI_GELU_GRAD) {
+    uint32_t zraw[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) zraw[c] = 0u;
+    if (row_ok) {
+      const bf16* zrow = ep.aux + static_cast<size_t>(row) * ep.ldaux + col0;
+      if (ep.vec_ok && col0 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 q4 = reinterpret_cast<const uint4*>(zrow)[i];
+          zraw[4 * i] = q4.x; zraw[4 * i + 1] = q4.y; zraw[4 * i + 2] = q4.z; zraw[4 * i + 3] = q4.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const uint32_t a = (col0 + 2 * c < N) ? __bfloat16_as_ushort(zrow[2 * c]) : 0u;
+          const uint32_t b = (col0 + 2 * c + 1 < N) ? __bfloat16_as_ushort(zrow[2 * c + 1]) : 0u;
+          zraw[c] = a | (b << 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const uint32_t raw = zraw[c >> 1];
+      const float z = __uint_as_float((c & 1) ? (raw & 0xffff0000u) : (raw << 16));
+      x[c] = v[c] * gelu_tanh_grad(z);
+    }
+  } else if (EPI == FACT_EPI_BIAS_GELU_SPLIT) {
+    float b[32];
+    load_bias32(b, ep, col0, N);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = gelu_tanh(v[c] + b[c]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (col0 + c < ep.scale_cols) ? v[c] * ep.scale : v[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const uint32_t hp = cvt_bf16x2(x[2 * c], x[2 * c + 1]);
+    o0[c] = hp;
+    o1[c] = cvt_bf16x2(x[2 * c] - __uint_as_float(hp << 16), x[2 * c + 1] - __uint_as_float(hp & 0xffff0000u));
+  }
+}
+
+template <int BN, int NPART, int STAGES, int EPI, bool TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_tc2_kernel(
     const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, int M, int N, int K,
+    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+    const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, int M, int N, int K,
     int tiles_n, int num_tiles, EpiArgs ep) {
-  using Cfg = Gemm2Cfg<BN, NPART, STAGES>;
+  using Cfg = Gemm2Cfg<BN, NPART, STAGES, TS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // TS: 8 x 4 KB, one slot per epilogue warp
+  const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -573,6 +680,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     if (NPART == 2) {
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmB1);
+    }
+    if (TS) {
+      tma_prefetch_desc(&tmO0);
+      tma_prefetch_desc(&tmO1);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 2);   // leader's arrive.expect_tx + peer's remote arrive
@@ -652,6 +763,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         }
       }
     }
+  } else if (TS) {  // ---------------- epilogue warps, bulk-store flavour: stage a 32 x 32 box, one TMA store per box
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t stg = staging_base + static_cast<uint32_t>(warp - 2) * TS_WARP_BYTES;
+    constexpr bool F32_OUT = EPI == FACT_EPI_BIAS_RESID_F32 || EPI == FACT_EPI_BIAS_F32;
+    const bool two = !F32_OUT && ep.out_lo != nullptr;
+    uint32_t t = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      const int m0 = (tile / tiles_n) * (2 * BM) + rank * BM, n0 = (tile % tiles_n) * BN;
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      const int row0 = m0 + q * 32, row = row0 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(tmem_full_bar(acc), acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N || row0 >= M) continue;  // warp-uniform: nothing of this box is inside the matrix
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        uint32_t o0[16], o1[16];
+        float of[32];
+        epilogue_compute<EPI>(v, row, col0, row_ok, N, ep, o0, o1, of);
+        if (lane == 0) bulk_wait_group_read0();  // the previous box of this warp has left the staging slot
+        __syncwarp();
+        if (F32_OUT) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk i of row r sits at chunk i ^ (r & 7)
+          const uint32_t rbase = stg + lane * 128, sw = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(rbase + ((i ^ sw) << 4), __float_as_uint(of[4 * i]), __float_as_uint(of[4 * i + 1]),
+                         __float_as_uint(of[4 * i + 2]), __float_as_uint(of[4 * i + 3]));
+        } else {  // 64-byte rows, SWIZZLE_64B: chunk i of row r sits at chunk i ^ ((r >> 1) & 3)
+          const uint32_t rbase = stg + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            st_shared_v4(rbase + ((i ^ sw) << 4), o0[4 * i], o0[4 * i + 1], o0[4 * i + 2], o0[4 * i + 3]);
+            if (two)
+              st_shared_v4(rbase + 2048 + ((i ^ sw) << 4), o1[4 * i], o1[4 * i + 1], o1[4 * i + 2], o1[4 * i + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (EPI == FACT_EPI_BIAS_RESID_F32 && ep.reduce_add) tma_reduce_add_2d(&tmO0, stg, col0, row0);
+          else tma_store_2d(&tmO0, stg, col0, row0);
+          if (two) tma_store_2d(&tmO1, stg + 2048, col0, row0);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tmem_empty_bar(acc));
+        else mbar_arrive_leader(tmem_empty_bar(acc));
+      }
+    }
+    if (lane == 0) bulk_wait_group0();  // all boxes written before the CTA (and its shared memory) goes away
   } else {  // ---------------- epilogue warps (both CTAs): this CTA's 128 rows of the pair tile
     const int q = warp & 3, half = (warp - 2) >> 2;
     uint32_t t = 0;
@@ -785,6 +953,33 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
   return FACT_OK;
 }
 
+// Output side of the TMA-store epilogue: row-major [rows, cols] of bf16 (elem_bytes 2) or fp32 (4), box 32 x 32,
+// swizzle span = the box's row bytes (64 / 128) so the row-per-lane staging writes are bank-conflict free.
+static int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, ld, 32, elem_bytes};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return FACT_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  FACT_REQUIRE(enc != nullptr, FACT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FACT_REQUIRE(r == CUDA_SUCCESS, FACT_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d) rows=%d cols=%d ld=%d",
+               static_cast<int>(r), rows, cols, ld);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return FACT_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -835,11 +1030,15 @@ static int launch_splitk(const CUtensorMap& a0, const CUtensorMap& a1, const CUt
   return FACT_OK;
 }
 
-template <int BN, int NPART, int STAGES, int EPI>
+struct OutMaps {
+  CUtensorMap o0, o1;
+};
+
+template <int BN, int NPART, int STAGES, int EPI, bool TS>
 static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
-                       int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
-  using Cfg = Gemm2Cfg<BN, NPART, STAGES>;
-  auto kern = gemm_tc2_kernel<BN, NPART, STAGES, EPI>;
+                       const OutMaps& om, int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN, NPART, STAGES, TS>;
+  auto kern = gemm_tc2_kernel<BN, NPART, STAGES, EPI, TS>;
   static bool attr_done = false;
   if (!attr_done) {
     FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -849,28 +1048,31 @@ static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   const int num_tiles = tiles_n * tiles_m;
   int clusters = num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, num_tiles, ep);
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, om.o0, om.o1, m, n, k, tiles_n, num_tiles,
+                                                            ep);
   FACT_LAUNCH_CHECK("gemm_tc2_kernel launch");
   return FACT_OK;
 }
 
-template <int BN, int NPART, int STAGES>
+template <int BN, int NPART, int STAGES, bool TS>
 static int launch_epi2(int kind, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                       const CUtensorMap& b1, int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
+                       const CUtensorMap& b1, const OutMaps& om, int m, int n, int k, const EpiArgs& ep,
+                       cudaStream_t st) {
   switch (kind) {
     case FACT_EPI_SPLIT:
-      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_SPLIT>(a0, a1, b0, b1, m, n, k, ep, st);
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_SPLIT, TS>(a0, a1, b0, b1, om, m, n, k, ep, st);
     case FACT_EPI_BIAS_GELU_SPLIT:
-      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_GELU_SPLIT>(a0, a1, b0, b1, m, n, k, ep, st);
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_GELU_SPLIT, TS>(a0, a1, b0, b1, om, m, n, k, ep, st);
     case FACT_EPI_BIAS_RESID_F32:
-      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_RESID_F32>(a0, a1, b0, b1, m, n, k, ep, st);
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_RESID_F32, TS>(a0, a1, b0, b1, om, m, n, k, ep, st);
     case FACT_EPI_BIAS_F32:
-      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_F32>(a0, a1, b0, b1, m, n, k, ep, st);
+      return launch_cfg2<BN, NPART, STAGES, FACT_EPI_BIAS_F32, TS>(a0, a1, b0, b1, om, m, n, k, ep, st);
     case FACT_EPI_BIAS_GELU_SAVE:
-      if (NPART == 1) return launch_cfg2<BN, 1, STAGES, FACT_EPI_BIAS_GELU_SAVE>(a0, a1, b0, b1, m, n, k, ep, st);
+      if (NPART == 1)
+        return launch_cfg2<BN, 1, STAGES, FACT_EPI_BIAS_GELU_SAVE, TS>(a0, a1, b0, b1, om, m, n, k, ep, st);
       break;
     case FACT_EPI_GELU_GRAD:
-      if (NPART == 1) return launch_cfg2<BN, 1, STAGES, FACT_EPI_GELU_GRAD>(a0, a1, b0, b1, m, n, k, ep, st);
+      if (NPART == 1) return launch_cfg2<BN, 1, STAGES, FACT_EPI_GELU_GRAD, TS>(a0, a1, b0, b1, om, m, n, k, ep, st);
       break;
   }
   set_error("epilogue kind %d unknown, or a training epilogue (4, 5) used with split (precise) operands", kind);
@@ -908,6 +1110,8 @@ int gemm_tile_n(int n) {
   return 128;
 }
 
+int g_gemm_tma_store = 1;  // fact_set_flag("gemm_tma_store", 0 | 1 | 2): pair-kernel epilogue through bulk tensor stores
+                           // (0 = direct row-per-lane stores, 2 = bulk stores but no in-place bulk reduction)
 int g_gemm_pair = 1;    // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
 int g_gemm_splitk = 1;  // fact_set_flag("gemm_splitk", 0) disables the small-M split-K path
 
@@ -952,6 +1156,7 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
   ep.seq_off = epi->seq_off;
   ep.aux = static_cast<const bf16*>(epi->aux);
   ep.ldaux = epi->ldaux;
+  ep.reduce_add = 0;
   if (split_out)
     ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
                 (!ep.bias || aligned16(ep.bias)) && (!ep.aux || (aligned16(ep.aux) && ep.ldaux % 8 == 0));
@@ -1004,12 +1209,35 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
     }
   }
   if (pair) {
-    if (precise) {
-      if (bn == 160) return launch_epi2<160, 2, 4>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
-      return launch_epi2<256, 2, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+    // epilogue through shared memory + bulk tensor stores when the output is a plain 16-byte-pitched matrix (no row
+    // remap); BIAS_RESID_F32 written in place becomes a bulk reduction (x += acc + bias inside the L2)
+    OutMaps om;
+    om.o0 = a0;
+    om.o1 = a0;
+    const int esz = split_out ? 2 : 4;
+    const void* out0 = split_out ? static_cast<const void*>(ep.out_hi) : static_cast<const void*>(ep.out_f32);
+    bool ts = g_gemm_tma_store != 0 && ep.seq_in == 0 && ep.vec_ok &&
+              (static_cast<long long>(ep.ldo) * esz) % 16 == 0 && aligned16(out0);
+    ep.reduce_add = 0;
+    if (ts && epi->kind == FACT_EPI_BIAS_RESID_F32 && g_gemm_tma_store == 1 && ep.resid == ep.out_f32 &&
+        ep.ldr == ep.ldo)
+      ep.reduce_add = 1;
+    if (ts) {
+      if ((rc = make_tmap_out(&om.o0, out0, m, n, ep.ldo, esz))) return rc;
+      if (split_out && ep.out_lo && (rc = make_tmap_out(&om.o1, ep.out_lo, m, n, ep.ldo, 2))) return rc;
+      if (precise) {
+        if (bn == 160) return launch_epi2<160, 2, 3, true>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
+        return launch_epi2<256, 2, 3, true>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
+      }
+      if (bn == 160) return launch_epi2<160, 1, 7, true>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
+      return launch_epi2<256, 1, 6, true>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
     }
-    if (bn == 160) return launch_epi2<160, 1, 8>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
-    return launch_epi2<256, 1, 6>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);
+    if (precise) {
+      if (bn == 160) return launch_epi2<160, 2, 4, false>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
+      return launch_epi2<256, 2, 3, false>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
+    }
+    if (bn == 160) return launch_epi2<160, 1, 8, false>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
+    return launch_epi2<256, 1, 6, false>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
   }
   if (precise) {
     if (bn == 160) return launch_epi<160, 2, 3>(epi->kind, a0, a1, b0, b1, m, n, k, ep, st);

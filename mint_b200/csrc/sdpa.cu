@@ -268,6 +268,7 @@ int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, 
 extern int g_gemm_pair;
 extern int g_gemm_splitk;
 extern int g_gemm_bn;
+extern int g_gemm_tma_store;
 extern int g_dual_stream;
 extern int g_ar_prune;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
@@ -291,6 +292,10 @@ extern "C" int fact_set_flag(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_bn") == 0) {
     g_gemm_bn = value;
+    return FACT_OK;
+  }
+  if (name && strcmp(name, "gemm_tma_store") == 0) {
+    g_gemm_tma_store = value;
     return FACT_OK;
   }
   if (name && strcmp(name, "gemm_splitk") == 0) {

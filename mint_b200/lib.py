@@ -98,6 +98,11 @@ def load():
         fn.restype, fn.argtypes = res, args
     from . import lib_bwd  # optional training symbols (same .so)
     lib_bwd.bind(lib)
+    # developer aid: FACT_FLAGS="gemm_tma_store=0,gemm_pair=1" -> fact_set_flag for A/B timing of kernel variants
+    for item in filter(None, os.environ.get("FACT_FLAGS", "").split(",")):
+        name, _, value = item.partition("=")
+        if lib.fact_set_flag(name.strip().encode(), int(value)) != 0:
+            raise FactError(f"FACT_FLAGS: unknown flag {name!r}")
     _lib = lib
     return lib
 

@@ -161,6 +161,68 @@ def test_gemm_pair_vs_single_bitwise(fact_lib, cuda):
 
 
 @pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32,
+                                  L.EPI_BIAS_GELU_SAVE, L.EPI_GELU_GRAD, "resid_inplace"])
+@pytest.mark.parametrize("m,n,k", [(700, 3072, 800), (360, 2400, 800), (1000, 320, 136), (300, 800, 3072)])
+def test_gemm_pair_tma_store_bitwise(fact_lib, cuda, m, n, k, kind, precise):
+    """The pair kernel's two epilogues -- direct row-per-lane stores (flag 0) and staged bulk tensor stores (1; 2 =
+    without the in-place bulk reduction) -- do the same arithmetic: identical bits, nothing written outside [m, n]."""
+    if kind in (L.EPI_BIAS_GELU_SAVE, L.EPI_GELU_GRAD) and precise:
+        pytest.skip("training epilogues take bf16 operands only")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda)
+    bias = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    resid = torch.randn(m, n, generator=g).to(cuda)
+    z = torch.randn(m, n, generator=g).to(cuda).to(torch.bfloat16)
+    a_hi, a_lo = split_ref(a)
+    w_hi, w_lo = split_ref(w)
+    pad = 64                                   # guard rows after the matrix: must stay NaN / sentinel
+    results = []
+    fact_lib.fact_set_flag(b"gemm_pair", 2)
+    try:
+        for flag in (0, 1, 2):
+            fact_lib.fact_set_flag(b"gemm_tma_store", flag)
+            e = L.GemmEpilogue()
+            e.bias = bias.data_ptr()
+            e.ldo = n
+            if kind == "resid_inplace":
+                out = torch.cat([resid.clone(), torch.full((pad, n), 7.0, device=cuda)])
+                e.kind, e.out_f32, e.resid, e.ldr = L.EPI_BIAS_RESID_F32, out.data_ptr(), out.data_ptr(), n
+                outs = (out,)
+            elif kind in (L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32):
+                out = torch.full((m + pad, n), 7.0, device=cuda)
+                e.kind, e.out_f32, e.resid, e.ldr = kind, out.data_ptr(), resid.data_ptr(), n
+                outs = (out,)
+            else:
+                o_hi = torch.full((m + pad, n), 7.0, dtype=torch.bfloat16, device=cuda)
+                o_lo = torch.full((m + pad, n), 7.0, dtype=torch.bfloat16, device=cuda)
+                e.kind, e.out_hi = kind, o_hi.data_ptr()
+                if kind != L.EPI_GELU_GRAD:
+                    e.out_lo = o_lo.data_ptr()
+                e.scale, e.scale_cols = 0.37, n // 3
+                e.aux, e.ldaux = z.data_ptr(), n
+                outs = (o_hi, o_lo)
+            L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, k, w_hi.data_ptr(),
+                                       w_lo.data_ptr() if precise else None, k, m, n, k, C.byref(e), _st()))
+            torch.cuda.synchronize()
+            for o in outs:
+                assert (o[m:].float() == 7.0).all(), f"flag {flag}: wrote past row {m}"
+            results.append([o.clone() for o in outs])
+    finally:
+        fact_lib.fact_set_flag(b"gemm_pair", 1)
+        fact_lib.fact_set_flag(b"gemm_tma_store", 1)
+    for r in results[1:]:
+        for o_ref, o in zip(results[0], r):
+            assert torch.equal(o_ref, o)
+    if kind == "resid_inplace":                # and the value is right, not merely consistent
+        a_eff = join(a_hi, a_lo).double() if precise else a_hi.double()
+        w_eff = join(w_hi, w_lo).double() if precise else w_hi.double()
+        ref = a_eff @ w_eff.t() + bias.double() + resid.double()
+        assert rel_err(results[1][0][:m].double(), ref) < 3e-5
+
+
+@pytest.mark.parametrize("precise", [True, False])
 @pytest.mark.parametrize("kind", [L.EPI_SPLIT, L.EPI_BIAS_GELU_SPLIT, L.EPI_BIAS_RESID_F32, L.EPI_BIAS_F32])
 @pytest.mark.parametrize("m,n,k", [(360, 2400, 800), (360, 800, 3072), (360, 3072, 800), (120, 800, 800),
                                    (128, 226, 800), (77, 128, 200)])
