@@ -36,7 +36,7 @@ extern "C" {
 #define FACT_MODE_BF16 1
 #define FACT_MODE_FP32_SIMT 2
 
-#define FACT_ABI_VERSION 1
+#define FACT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FACT_API __attribute__((visibility("default")))
@@ -164,6 +164,9 @@ typedef struct fact_gemm_epilogue {
    * splits * m * n * 4 bytes, the library uses as many splits as fit.  NULL = never split. */
   void* splitk_scratch;
   size_t splitk_scratch_bytes;
+  /* FACT_EPI_GELU_GRAD, optional: colsum[c] += sum over rows of the bf16 output (the bias gradient of the FFN hidden
+   * layer) -- folded into the epilogue instead of a second pass over the [m, n] output.  fp32 [n], NULL = skip. */
+  float* colsum;
 } fact_gemm_epilogue;
 
 /* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).

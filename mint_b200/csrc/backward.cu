@@ -123,20 +123,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(
 }
 
 // =========================================================================================== attention backward
-// D[b,h,row] = sum_d dO * O  (softmax-backward row term), one warp per (token, head)
+// D[b,h,row] = sum_d dO * O  (softmax-backward row term).  One warp per token: 16-byte loads across the whole
+// [H * DH] row (DH % 8 == 0, so a chunk never straddles heads), per-chunk partial dots reduced per head through
+// shared memory.
 __global__ void __launch_bounds__(256) sdpa_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                                                             float* __restrict__ Dv, int tokens, int N, int H, int DH) {
-  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (gw >= tokens * H) return;
-  const int tok = gw / H, h = gw % H;
-  const bf16* po = o + static_cast<size_t>(tok) * H * DH + h * DH;
-  const bf16* pd = d_o + static_cast<size_t>(tok) * H * DH + h * DH;
-  float s = 0.f;
-  for (int i = lane; i < DH; i += 32) s += __bfloat162float(po[i]) * __bfloat162float(pd[i]);
+  __shared__ float part[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * 8 + warp;
+  if (tok >= tokens) return;
+  const int chunks = H * DH / 8, cph = DH / 8;  // chunks <= 128 (d_model <= 1024)
+  const uint4* po = reinterpret_cast<const uint4*>(o + static_cast<size_t>(tok) * H * DH);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + static_cast<size_t>(tok) * H * DH);
+  for (int c = lane; c < chunks; c += 32) {
+    const uint4 a = po[c], b = pd[c];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    float s = 0.f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) {
-    const int b = tok / N, r = tok % N;
+    for (int i = 0; i < 4; ++i) {
+      s = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), s);
+      s = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(bw[i] & 0xffff0000u), s);
+    }
+    part[warp][c] = s;
+  }
+  __syncwarp();
+  const int b = tok / N, r = tok % N;
+  for (int h = lane; h < H; h += 32) {
+    float s = 0.f;
+    for (int i = 0; i < cph; ++i) s += part[warp][h * cph + i];
     Dv[(static_cast<size_t>(b) * H + h) * N + r] = s;
   }
 }
@@ -347,80 +361,85 @@ __global__ void __launch_bounds__(256) sdpa_bwd_finish_kernel(const float* __res
 }
 
 // =========================================================================================== LayerNorm backward
-// Two bandwidth-shaped passes (the one-pass version needed 154 registers -> 8 warps/SM and ran at 1/4 of HBM speed):
-//  (1) ln_bwd_stats_kernel: one warp per row -> stats[row] = {mean, rstd, mean(g*dy), mean(g*dy*xhat)}
-//  (2) ln_bwd_apply_kernel: thread = one float4 column group, block = a slab of rows: dx = dres + rstd*(g*dy - m1 -
-//      xhat*m2), dgamma / dbeta partial sums live in 8 registers and leave through one atomicAdd per column per block.
-__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                           const float* __restrict__ dy, float4* __restrict__ stats,
-                                                           int rows, int d) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= rows) return;
-  const int nv = d >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
-  const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * d);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 v[8];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = lane + i * 32;
-    v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / d;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (lane + i * 32 < nv) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / d + 1e-5f);
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      const float4 dyv = yr[idx];
-      const float4 gg = __ldg(g4 + idx);
-      const float a0 = gg.x * dyv.x, a1 = gg.y * dyv.y, a2 = gg.z * dyv.z, a3 = gg.w * dyv.w;
-      s1 += (a0 + a1) + (a2 + a3);
-      s2 += (a0 * v[i].x + a1 * v[i].y) + (a2 * v[i].z + a3 * v[i].w);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane == 0) stats[row] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
-}
-
+// One launch, two phases per 32-row slab (HBM sees x, dy and dres once: the second phase re-reads x / dy from L1 / L2):
+//  (1) one warp per row: stats[row] = {mean, rstd, mean(g*dy), rstd * mean(g*dy*xhat)} into shared memory
+//  (2) thread = one float4 column group: dx = dres + rstd*(g*dy - m1 - xhat*m2); dgamma / dbeta (and, optionally, the
+//      column sums of dx = the bias gradient of the dense layer that produced x's residual branch) stay in registers
+//      and leave through one atomicAdd per column per block; dx is optionally also written as the bf16 GEMM operand.
+// (A one-pass register-resident version needed 154 registers -> 8 warps/SM and ran at a quarter of HBM speed.)
 constexpr int LN_ROWS_PER_BLOCK = 32;
-__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                           const float* __restrict__ dy, const float* __restrict__ dres,
-                                                           const float4* __restrict__ stats, float* __restrict__ dx,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           int rows, int d) {
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ dy, const float* dres, float* dx,
+                                                     bf16* __restrict__ dx_b, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, float* __restrict__ colsum, int rows,
+                                                     int d) {
+  __shared__ float4 sstats[LN_ROWS_PER_BLOCK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = d >> 2;
-  const int cg = threadIdx.x;  // column group (d <= 1024 -> nv <= 256)
-  if (cg >= nv) return;
   const int r0 = blockIdx.x * LN_ROWS_PER_BLOCK;
   const int r1 = min(rows, r0 + LN_ROWS_PER_BLOCK);
-  const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + cg);
-  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  // ---- phase 1
+  for (int row = r0 + warp; row < r1; row += 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
+    const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * d);
+    float4 v[8], u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + i * 32;
+      v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + i * 32;
+      u[i] = idx < nv ? yr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane + i * 32 < nv) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / d + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float4 gg = __ldg(g4 + idx);
+        const float a0 = gg.x * u[i].x, a1 = gg.y * u[i].y, a2 = gg.z * u[i].z, a3 = gg.w * u[i].w;
+        s1 += (a0 + a1) + (a2 + a3);
+        s2 += (a0 * v[i].x + a1 * v[i].y) + (a2 * v[i].z + a3 * v[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) sstats[row - r0] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
+  }
+  __syncthreads();
+  // ---- phase 2
+  const int cg = threadIdx.x;  // column group (d <= 1024 -> nv <= 256)
+  if (cg >= nv) return;
+  const float4 gg = __ldg(g4 + cg);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
 #pragma unroll 4
   for (int r = r0; r < r1; ++r) {
     const size_t off = static_cast<size_t>(r) * nv + cg;
     const float4 xv = reinterpret_cast<const float4*>(x)[off];
     const float4 dyv = reinterpret_cast<const float4*>(dy)[off];
-    const float4 st = __ldg(stats + r);  // mean, rstd, m1, m2
+    const float4 st = sstats[r - r0];  // mean, rstd, m1, m2
     float4 xh;
     xh.x = (xv.x - st.x) * st.y; xh.y = (xv.y - st.x) * st.y; xh.z = (xv.z - st.x) * st.y; xh.w = (xv.w - st.x) * st.y;
     float4 o;
@@ -433,13 +452,19 @@ __global__ void __launch_bounds__(256) ln_bwd_apply_kernel(const float* __restri
       o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
     }
     reinterpret_cast<float4*>(dx)[off] = o;
+    if (dx_b) reinterpret_cast<uint2*>(dx_b)[off] = make_uint2(cvt_bf16x2(o.x, o.y), cvt_bf16x2(o.z, o.w));
     ag.x += dyv.x * xh.x; ag.y += dyv.y * xh.y; ag.z += dyv.z * xh.z; ag.w += dyv.w * xh.w;
     ab.x += dyv.x; ab.y += dyv.y; ab.z += dyv.z; ab.w += dyv.w;
+    ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
   }
   atomicAdd(dgamma + cg * 4 + 0, ag.x); atomicAdd(dgamma + cg * 4 + 1, ag.y);
   atomicAdd(dgamma + cg * 4 + 2, ag.z); atomicAdd(dgamma + cg * 4 + 3, ag.w);
   atomicAdd(dbeta + cg * 4 + 0, ab.x); atomicAdd(dbeta + cg * 4 + 1, ab.y);
   atomicAdd(dbeta + cg * 4 + 2, ab.z); atomicAdd(dbeta + cg * 4 + 3, ab.w);
+  if (colsum) {
+    atomicAdd(colsum + cg * 4 + 0, ac.x); atomicAdd(colsum + cg * 4 + 1, ac.y);
+    atomicAdd(colsum + cg * 4 + 2, ac.z); atomicAdd(colsum + cg * 4 + 3, ac.w);
+  }
 }
 
 // =========================================================================================== cast + column sums
@@ -617,10 +642,18 @@ __global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------- internal launchers
+int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dW, int ldw, int tokens, int in_dim,
+                    int out_dim, cudaStream_t st, bool* done);  // wgrad_tc.cu
+
 int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dW, int ldw, int tokens, int in_dim,
                int out_dim, cudaStream_t st) {
   FACT_REQUIRE(x_bf16 && dy_bf16 && dW && tokens > 0 && in_dim > 0 && out_dim > 0, FACT_ERR_BAD_SHAPE,
                "wgrad_gemm: bad arguments");
+  {
+    bool done = false;  // large problems: 256 x 256 CTA-pair tiles
+    const int rc2 = wgrad_gemm_pair(x_bf16, ldx, dy_bf16, ldy, dW, ldw, tokens, in_dim, out_dim, st, &done);
+    if (rc2 != FACT_OK || done) return rc2;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     FACT_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
@@ -655,8 +688,8 @@ int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* 
   const long long tokens = static_cast<long long>(batch) * n;
   FACT_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, tokens * d * sizeof(float), st));
   {
-    const long long warps = tokens * heads;
-    sdpa_bwd_prep_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(
+    FACT_REQUIRE(d <= 1024, FACT_ERR_UNSUPPORTED, "sdpa_backward: d_model %d", d);
+    sdpa_bwd_prep_kernel<<<static_cast<int>((tokens + 7) / 8), 256, 0, st>>>(
         static_cast<const bf16*>(o), static_cast<const bf16*>(d_o), Dv, static_cast<int>(tokens), n, heads, head_dim);
     FACT_LAUNCH_CHECK("sdpa_bwd_prep_kernel");
   }
@@ -689,15 +722,15 @@ int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* 
   return FACT_OK;
 }
 
-int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, float* dgamma,
-                float* dbeta, float* stats, int rows, int d, cudaStream_t st) {
+// dx_b (bf16 copy of dx) and colsum (+= column sums of dx) are optional: they fold the cast_colsum pass that would
+// otherwise re-read dx for the next dense layer's weight / bias gradients into this kernel
+int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, void* dx_b,
+                float* dgamma, float* dbeta, float* colsum, int rows, int d, cudaStream_t st) {
   FACT_REQUIRE(d % 4 == 0 && d <= 1024, FACT_ERR_BAD_SHAPE, "ln_backward: d %d", d);
-  FACT_REQUIRE(stats != nullptr, FACT_ERR_BAD_SHAPE, "ln_backward: stats scratch missing");
-  ln_bwd_stats_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, dy, reinterpret_cast<float4*>(stats), rows, d);
-  FACT_LAUNCH_CHECK("ln_bwd_stats_kernel");
-  ln_bwd_apply_kernel<<<(rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK, 256, 0, st>>>(
-      x, gamma, dy, dres, reinterpret_cast<const float4*>(stats), dx, dgamma, dbeta, rows, d);
-  FACT_LAUNCH_CHECK("ln_bwd_apply_kernel");
+  FACT_REQUIRE(dy != dx, FACT_ERR_BAD_SHAPE, "ln_backward: dx must not alias dy (it may alias dres)");
+  ln_bwd_kernel<<<(rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK, 256, 0, st>>>(
+      x, gamma, dy, dres, dx, static_cast<bf16*>(dx_b), dgamma, dbeta, colsum, rows, d);
+  FACT_LAUNCH_CHECK("ln_bwd_kernel");
   return FACT_OK;
 }
 
@@ -782,7 +815,8 @@ extern "C" int fact_layernorm_backward(const float* x, const float* gamma, const
                                        void* stream) {
   FACT_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && stats_scratch && rows > 0, FACT_ERR_BAD_SHAPE,
                "fact_layernorm_backward: bad arguments");
-  return ln_backward(x, gamma, dy, dres, dx, dgamma, dbeta, stats_scratch, rows, d, as_stream(stream));
+  (void)stats_scratch;  // kept in the signature; the row statistics now live in shared memory
+  return ln_backward(x, gamma, dy, dres, dx, nullptr, dgamma, dbeta, nullptr, rows, d, as_stream(stream));
 }
 
 extern "C" int fact_embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dw, float* dbias,

@@ -18,8 +18,8 @@ int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float*
                int out_dim, cudaStream_t st);
 int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* Dv, float* dq_acc,
                   void* dqkv, int batch, int n, int heads, int head_dim, float scale, cudaStream_t st);
-int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, float* dgamma,
-                float* dbeta, float* stats, int rows, int d, cudaStream_t st);
+int ln_backward(const float* x, const float* gamma, const float* dy, const float* dres, float* dx, void* dx_b,
+                float* dgamma, float* dbeta, float* colsum, int rows, int d, cudaStream_t st);
 int cast_colsum(const float* x, int ldx, void* y, int ldy, float* colsum, int rows, int n, cudaStream_t st);
 int colsum_bf16(const void* x, int ldx, float* colsum, int rows, int n, cudaStream_t st);
 int slice_rows(const float* src, float* dst, long long rows_dst, int d, int seq_dst, int seq_src, int seq_off,
@@ -158,31 +158,35 @@ static int layer_fwd_train(const fact_dims* dm, const fact_layer_weights& L, con
   return bf16_gemm(S.h, ff, L.w2_hi, ff, M, d, ff, &e, st);
 }
 
-// backward of one layer: dy [M, d] fp32 holds dL/d(output) on entry and dL/d(input) on exit
+// backward of one layer: dy [M, d] fp32 holds dL/d(output) on entry and dL/d(input) on exit.
+// dy_b_ready: ws.dy_b already holds bf16(dy) and G.b2 already has its column sums (the LayerNorm backward of the layer
+// above wrote them); next_b2: bias gradient the layer below wants from this layer's output (NULL: it casts itself).
 static int layer_bwd(const fact_dims* dm, const fact_layer_weights& L, const fact_layer_grads& G, const SavedLayer& S,
-                     int batch, int seq, float* dy, const TrainWs& ws, cudaStream_t st) {
+                     int batch, int seq, float* dy, const TrainWs& ws, bool dy_b_ready, float* next_b2,
+                     cudaStream_t st) {
   const int d = dm->d_model, ff = dm->d_ff, H = dm->n_heads, dh = d / H, M = batch * seq;
   int rc;
   fact_gemm_epilogue e{};
   // ---- Residual(Norm(MLP))
-  if ((rc = cast_colsum(dy, d, ws.dy_b, d, G.b2, M, d, st))) return rc;
+  if (!dy_b_ready && (rc = cast_colsum(dy, d, ws.dy_b, d, G.b2, M, d, st))) return rc;
   if ((rc = wgrad_gemm(S.h, ff, ws.dy_b, d, G.w2, d, M, ff, d, st))) return rc;
   e.kind = FACT_EPI_GELU_GRAD;
   e.out_hi = ws.dz_b;
   e.ldo = ff;
   e.aux = S.hpre;
   e.ldaux = ff;
+  e.colsum = G.b1;  // d b1 = column sums of dz, taken in the same epilogue
   if ((rc = bf16_gemm(ws.dy_b, d, L.w2_kl, d, M, ff, d, &e, st))) return rc;  // dh = dy . W2^T, then * gelu'(z)
-  if ((rc = colsum_bf16(ws.dz_b, ff, G.b1, M, ff, st))) return rc;
   if ((rc = wgrad_gemm(S.ln2, d, ws.dz_b, ff, G.w1, ff, M, d, ff, st))) return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_BIAS_F32;
   e.out_f32 = ws.dln;
   e.ldo = d;
   if ((rc = bf16_gemm(ws.dz_b, ff, L.w1_kl, ff, M, d, ff, &e, st))) return rc;  // d ln2 = dz . W1^T
-  if ((rc = ln_backward(S.x_mid, L.ln2_gamma, ws.dln, dy, dy, G.ln2_gamma, G.ln2_beta, ws.ln_stats, M, d, st))) return rc;
-  // ---- Residual(Norm(Attention)): dy is now dL/d x_mid
-  if ((rc = cast_colsum(dy, d, ws.dy_b, d, G.bo, M, d, st))) return rc;
+  // dy becomes dL/d x_mid; its bf16 copy and column sums (= d bo) come out of the same pass
+  if ((rc = ln_backward(S.x_mid, L.ln2_gamma, ws.dln, dy, dy, ws.dy_b, G.ln2_gamma, G.ln2_beta, G.bo, M, d, st)))
+    return rc;
+  // ---- Residual(Norm(Attention))
   if ((rc = wgrad_gemm(S.ao, d, ws.dy_b, d, G.wo, d, M, d, d, st))) return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_SPLIT;
@@ -200,7 +204,8 @@ static int layer_bwd(const fact_dims* dm, const fact_layer_weights& L, const fac
   e.out_f32 = ws.dln;
   e.ldo = d;
   if ((rc = bf16_gemm(ws.dqkv_b, 3 * d, L.wqkv_kl, 3 * d, M, d, 3 * d, &e, st))) return rc;  // d ln1 = dqkv . Wqkv^T
-  return ln_backward(S.x_in, L.ln1_gamma, ws.dln, dy, dy, G.ln1_gamma, G.ln1_beta, ws.ln_stats, M, d, st);
+  return ln_backward(S.x_in, L.ln1_gamma, ws.dln, dy, dy, next_b2 ? ws.dy_b : nullptr, G.ln1_gamma, G.ln1_beta, next_b2,
+                     M, d, st);
 }
 
 }  // namespace fact
@@ -285,7 +290,9 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   e.ldo = d;
   if ((rc = bf16_gemm(ws.dpred_b, odp, w->out_w_kl, odp, Mc, d, odp, &e, st))) return rc;  // d xf = dpred . Wout^T
   for (int l = dims->cross_layers - 1; l >= 0; --l)
-    if ((rc = layer_bwd(dims, w->cross_layers[l], g->cross_layers[l], Sc[l], batch, ns, ws.dy, ws, st))) return rc;
+    if ((rc = layer_bwd(dims, w->cross_layers[l], g->cross_layers[l], Sc[l], batch, ns, ws.dy, ws,
+                        l + 1 < dims->cross_layers, l > 0 ? g->cross_layers[l - 1].b2 : nullptr, st)))
+      return rc;
   // tf.concat backward (base_models.py:192-193): rows [0, motion_seq) -> motion encoder, the rest -> audio encoder
   if ((rc = slice_rows(ws.dy, ws.dym, static_cast<long long>(batch) * dims->motion_seq, d, dims->motion_seq, ns, 0, st)))
     return rc;
@@ -293,10 +300,12 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
                        dims->motion_seq, st)))
     return rc;
   for (int l = dims->motion_layers - 1; l >= 0; --l)
-    if ((rc = layer_bwd(dims, w->motion_layers[l], g->motion_layers[l], Sm[l], batch, dims->motion_seq, ws.dym, ws, st)))
+    if ((rc = layer_bwd(dims, w->motion_layers[l], g->motion_layers[l], Sm[l], batch, dims->motion_seq, ws.dym, ws,
+                        l + 1 < dims->motion_layers, l > 0 ? g->motion_layers[l - 1].b2 : nullptr, st)))
       return rc;
   for (int l = dims->audio_layers - 1; l >= 0; --l)
-    if ((rc = layer_bwd(dims, w->audio_layers[l], g->audio_layers[l], Sa[l], batch, dims->audio_seq, ws.dya, ws, st)))
+    if ((rc = layer_bwd(dims, w->audio_layers[l], g->audio_layers[l], Sa[l], batch, dims->audio_seq, ws.dya, ws,
+                        l + 1 < dims->audio_layers, l > 0 ? g->audio_layers[l - 1].b2 : nullptr, st)))
       return rc;
   if ((rc = embed_backward(motion, static_cast<long long>(dims->motion_seq) * dims->motion_dim, ws.dym,
                            g->motion_embed_w, g->motion_embed_b, g->motion_pos, batch, dims->motion_seq,

@@ -43,6 +43,7 @@ struct EpiArgs {
   const bf16* aux;  // GELU_GRAD: saved pre-activation
   int ldaux;
   int reduce_add;  // TMA-store epilogue, BIAS_RESID_F32 with out == resid: the add is a bulk reduction in the L2
+  float* colsum;   // TMA-store epilogue, GELU_GRAD: += column sums of the staged bf16 box (bias gradient)
 };
 
 template <int BN, int NPART, int STAGES>
@@ -811,6 +812,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
           if (two) tma_store_2d(&tmO1, stg + 2048, col0, row0);
           bulk_commit_group();
         }
+        if (EPI == FACT_EPI_GELU_GRAD && ep.colsum != nullptr) {
+          // bias gradient: lane c sums column c of the staged box (rows past M hold zeros), one atomic per column
+          float s = 0.f;
+          const uint32_t cb = stg + (lane & 7) * 2;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            uint16_t hv;
+            asm volatile("ld.shared.u16 %0, [%1];"
+                         : "=h"(hv)
+                         : "r"(cb + r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4)));
+            s += __uint_as_float(static_cast<uint32_t>(hv) << 16);
+          }
+          if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, s);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -955,7 +970,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
 
 // Output side of the TMA-store epilogue: row-major [rows, cols] of bf16 (elem_bytes 2) or fp32 (4), box 32 x 32,
 // swizzle span = the box's row bytes (64 / 128) so the row-per-lane staging writes are bank-conflict free.
-static int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes) {
+int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey key{ptr, rows, cols, ld, 32, elem_bytes};
   auto it = cache.find(key);
@@ -1121,9 +1136,25 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 using namespace fact;
 
+namespace fact {
+int colsum_bf16(const void* x, int ldx, float* colsum, int rows, int n, cudaStream_t st);  // backward.cu
+}
+
+static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                         int m, int n, int k, const fact_gemm_epilogue* epi, void* stream, bool* colsum_fused);
+
 extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
                          int m, int n, int k, const fact_gemm_epilogue* epi, void* stream) {
   FACT_REQUIRE(a_hi && w_hi && epi, FACT_ERR_BAD_SHAPE, "fact_gemm: null operand");
+  bool colsum_fused = false;
+  int rc = gemm_dispatch(a_hi, a_lo, lda, w_hi, w_lo, ldw, m, n, k, epi, stream, &colsum_fused);
+  if (rc == FACT_OK && epi->kind == FACT_EPI_GELU_GRAD && epi->colsum && !colsum_fused)
+    rc = colsum_bf16(epi->out_hi, epi->ldo, epi->colsum, m, n, as_stream(stream));  // kernels without the fused sums
+  return rc;
+}
+
+static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                         int m, int n, int k, const fact_gemm_epilogue* epi, void* stream, bool* colsum_fused) {
   FACT_REQUIRE(m > 0 && n > 0 && k > 0, FACT_ERR_BAD_SHAPE, "fact_gemm: bad shape m=%d n=%d k=%d", m, n, k);
   FACT_REQUIRE((a_lo == nullptr) == (w_lo == nullptr), FACT_ERR_BAD_SHAPE,
                "fact_gemm: a_lo and w_lo must both be given (precise) or both be NULL (bf16)");
@@ -1157,6 +1188,7 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
   ep.aux = static_cast<const bf16*>(epi->aux);
   ep.ldaux = epi->ldaux;
   ep.reduce_add = 0;
+  ep.colsum = nullptr;
   if (split_out)
     ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
                 (!ep.bias || aligned16(ep.bias)) && (!ep.aux || (aligned16(ep.aux) && ep.ldaux % 8 == 0));
@@ -1223,6 +1255,10 @@ extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void
         ep.ldr == ep.ldo)
       ep.reduce_add = 1;
     if (ts) {
+      if (epi->kind == FACT_EPI_GELU_GRAD && epi->colsum) {
+        ep.colsum = epi->colsum;
+        *colsum_fused = true;
+      }
       if ((rc = make_tmap_out(&om.o0, out0, m, n, ep.ldo, esz))) return rc;
       if (split_out && ep.out_lo && (rc = make_tmap_out(&om.o1, ep.out_lo, m, n, ep.ldo, 2))) return rc;
       if (precise) {

@@ -269,6 +269,7 @@ extern int g_gemm_pair;
 extern int g_gemm_splitk;
 extern int g_gemm_bn;
 extern int g_gemm_tma_store;
+extern int g_wgrad_pair;
 extern int g_dual_stream;
 extern int g_ar_prune;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
@@ -292,6 +293,10 @@ extern "C" int fact_set_flag(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_bn") == 0) {
     g_gemm_bn = value;
+    return FACT_OK;
+  }
+  if (name && strcmp(name, "wgrad_pair") == 0) {
+    g_wgrad_pair = value;
     return FACT_OK;
   }
   if (name && strcmp(name, "gemm_tma_store") == 0) {

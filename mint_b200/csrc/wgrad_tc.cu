@@ -1,0 +1,233 @@
+// Weight-gradient GEMM on CTA pairs: dW[in, out] += X^T . dY over the tokens (reference semantics: tape.gradient of the
+// Dense kernels, mint/ctl/single_task_trainer.py:176-178).
+//
+// The 1-SM kernel in backward.cu (128 x 128 tiles) needs 128 bytes of operands per MMA clock and is bound by the
+// L2 -> SM path at a third of the tensor peak.  Here a cluster of two CTAs owns a 256 x 256 tile (cta_group::2: each CTA
+// stages its own 128 `in` rows of X^T and 128 of the 256 `out` columns of dY), which halves the operand bytes per flop:
+//   * both operands MN-major straight from the row-major activations through TMA ({64 MN, 64 tokens} SWIZZLE_128B boxes;
+//     boxes past the matrix edge are zero-filled on chip and cost no L2 traffic),
+//   * persistent clusters walk (tile, token-slice) work items; two 256-column TMEM accumulators, so the epilogue of one
+//     item overlaps the main loop of the next,
+//   * epilogue: each warp stages a 32 x 32 fp32 box in shared memory and the TMA engine adds it into dW in the L2
+//     (cp.reduce.async.bulk .add.f32) -- no row-strided atomics through the LSU.
+#include "fact_internal.h"
+#include "fact_ptx.cuh"
+
+namespace fact {
+
+constexpr int W2_BK = 64, W2_STAGES = 6, W2_EPI_WARPS = 8, W2_THREADS = 64 + W2_EPI_WARPS * 32;
+constexpr int W2_BOX_BYTES = 64 * 64 * 2;           // one {64 MN, 64 tokens} box
+constexpr int W2_STAGE_BYTES = 4 * W2_BOX_BYTES;    // per CTA: A 128 rows (2 boxes) + B 128 columns (2 boxes)
+constexpr int W2_STAGING_BYTES = W2_EPI_WARPS * 4096;
+constexpr int W2_SMEM_BYTES = 1024 + W2_STAGES * W2_STAGE_BYTES + W2_STAGING_BYTES + 256;
+static_assert(W2_SMEM_BYTES <= 232448, "exceeds 227 KB");
+
+// tmX: {in (inner), tokens}, tmY: {out (inner), tokens}, tmW: fp32 dW {out (inner), in}, box 32 x 32 SWIZZLE_128B.
+// Work item w -> (tile = w / splits, slice = w % splits); slice z covers token blocks [z * kb_per, (z + 1) * kb_per).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_wgrad2_kernel(
+    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+    const __grid_constant__ CUtensorMap tmW, int IN, int OUT, int tiles_out, int num_items, int splits, int num_kb,
+    int kb_per) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t staging_base = smem_base + W2_STAGES * W2_STAGE_BYTES;
+  const uint32_t bar_base = staging_base + W2_STAGING_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (W2_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * W2_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * W2_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * W2_STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + W2_STAGES * W2_STAGE_BYTES + W2_STAGING_BYTES + 8 * (2 * W2_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < W2_STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // leader's arrive.expect_tx + peer's remote arrive
+      mbar_init(empty_bar(s), 1);  // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 2 * W2_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_ptr_addr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  auto sA = [&](int s) { return smem_base + s * W2_STAGE_BYTES; };
+  auto sB = [&](int s) { return smem_base + s * W2_STAGE_BYTES + 2 * W2_BOX_BYTES; };
+  auto item_kb = [&](int item, int& kb0) {
+    kb0 = (item % splits) * kb_per;
+    const int kb1 = min(kb0 + kb_per, num_kb);
+    return kb1 - kb0;  // >= 1 by construction of splits / kb_per
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs)
+    uint32_t it = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int tile = item / splits;
+      const int m0 = (tile / tiles_out) * 256 + rank * 128;  // this CTA's `in` rows
+      const int n0 = (tile % tiles_out) * 256 + rank * 128;  // this CTA's half of the `out` columns
+      int kb0;
+      const int nkb = item_kb(item, kb0);
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % W2_STAGES;
+        mbar_wait(empty_bar(s), ((it / W2_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * W2_STAGE_BYTES);
+          else mbar_arrive_leader(full_bar(s));
+          const int t0 = (kb0 + i) * W2_BK;
+          tma_load_2d_2sm(sA(s), &tmX, m0, t0, full_bar(s));
+          tma_load_2d_2sm(sA(s) + W2_BOX_BYTES, &tmX, m0 + 64, t0, full_bar(s));
+          tma_load_2d_2sm(sB(s), &tmY, n0, t0, full_bar(s));
+          tma_load_2d_2sm(sB(s) + W2_BOX_BYTES, &tmY, n0 + 64, t0, full_bar(s));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {  // ---------------- MMA issuer
+      constexpr uint32_t idesc = umma_idesc_bf16_f32_maj(256, 256, 1, 1);
+      uint32_t it = 0, t = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++t) {
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        int kb0;
+        const int nkb = item_kb(item, kb0);
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % W2_STAGES;
+          mbar_wait(full_bar(s), (it / W2_STAGES) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a0 = umma_desc_mn_sw128(sA(s), W2_BOX_BYTES, 1024);
+            const uint64_t b0 = umma_desc_mn_sw128(sB(s), W2_BOX_BYTES, 1024);
+#pragma unroll
+            for (int kk = 0; kk < W2_BK / 16; ++kk) {  // 16 tokens = two 8-row groups = 2048 bytes
+              const uint64_t off = static_cast<uint64_t>(kk * 2048) >> 4;
+              umma_bf16_2sm(tmem_d, a0 + off, b0 + off, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(empty_bar(s), 0x3);
+            if (i == nkb - 1) umma_commit_2sm(tmem_full_bar(acc), 0x3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (both CTAs): this CTA's 128 `in` rows x 256 `out` columns
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t stg = staging_base + static_cast<uint32_t>(warp - 2) * 4096;
+    uint32_t t = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++t) {
+      const int tile = item / splits;
+      const int row0 = (tile / tiles_out) * 256 + rank * 128 + q * 32;
+      const int n0 = (tile % tiles_out) * 256;
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      mbar_wait(tmem_full_bar(acc), acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < 8; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= OUT || row0 >= IN) continue;
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + c * 32, v);
+        tmem_ld_wait();
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+        const uint32_t rbase = stg + lane * 128, sw = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          st_shared_v4(rbase + ((i ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                       __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmW, stg, col0, row0);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tmem_empty_bar(acc));
+        else mbar_arrive_leader(tmem_empty_bar(acc));
+      }
+    }
+    if (lane == 0) bulk_wait_group0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+int g_wgrad_pair = 1;  // fact_set_flag("wgrad_pair", 0): keep the 1-SM 128 x 128 kernel (A/B timing, tests)
+
+// returns FACT_OK and sets *done when the pair kernel took the problem; *done = false -> caller uses the 1-SM kernel
+int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dW, int ldw, int tokens, int in_dim,
+                    int out_dim, cudaStream_t st, bool* done) {
+  *done = false;
+  // bulk reductions need a 16-byte pitch; tiny or skinny problems stay on the 128 x 128 kernel
+  if (!g_wgrad_pair || (static_cast<long long>(ldw) * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(dW) & 15) != 0 ||
+      in_dim < 256 || out_dim < 256 || tokens < 64 * 64)
+    return FACT_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap tmx, tmy, tmw;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmx, x_bf16, tokens, in_dim, ldx, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tmy, dy_bf16, tokens, out_dim, ldy, 64, 64))) return rc;
+  if ((rc = make_tmap_out(&tmw, dW, in_dim, out_dim, ldw, 4))) return rc;
+  const int tiles_in = (in_dim + 255) / 256, tiles_out = (out_dim + 255) / 256;
+  const int tiles = tiles_in * tiles_out;
+  const int num_kb = (tokens + W2_BK - 1) / W2_BK;
+  const int clusters_max = num_sms() / 2;
+  // token slices: the split that fills whole rounds of the persistent clusters best, with >= 24 token blocks per item
+  // so the 256 KB reduction per item stays a small fraction of the main loop
+  int best_s = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 64 && num_kb / s >= 24; ++s) {
+    const int kbp = (num_kb + s - 1) / s;
+    const int s_eff = (num_kb + kbp - 1) / kbp;
+    const int items = tiles * s_eff;
+    const int rounds = (items + clusters_max - 1) / clusters_max;
+    const double eff = static_cast<double>(items) / (static_cast<double>(rounds) * clusters_max);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_s = s_eff;
+    }
+  }
+  const int kb_per = (num_kb + best_s - 1) / best_s;
+  const int splits = (num_kb + kb_per - 1) / kb_per;
+  const int num_items = tiles * splits;
+  const int clusters = num_items < clusters_max ? num_items : clusters_max;
+  gemm_wgrad2_kernel<<<2 * clusters, W2_THREADS, W2_SMEM_BYTES, st>>>(tmx, tmy, tmw, in_dim, out_dim, tiles_out,
+                                                                      num_items, splits, num_kb, kb_per);
+  FACT_LAUNCH_CHECK("gemm_wgrad2_kernel launch");
+  *done = true;
+  return FACT_OK;
+}
+
+}  // namespace fact

@@ -50,10 +50,14 @@ class Grads(C.Structure):
         "out_w", "out_b")]
 
 
+ABI_VERSION = 2  # FACT_ABI_VERSION of include/fact_sm100.h these ctypes declarations mirror
+
+
 class GemmEpilogue(C.Structure):
     _fields_ = [("kind", _i), ("out_f32", _vp), ("out_hi", _vp), ("out_lo", _vp), ("ldo", _i), ("bias", _vp),
                 ("resid", _vp), ("ldr", _i), ("scale", _f), ("scale_cols", _i), ("seq_in", _i), ("seq_out", _i),
-                ("seq_off", _i), ("aux", _vp), ("ldaux", _i), ("splitk_scratch", _vp), ("splitk_scratch_bytes", C.c_size_t)]
+                ("seq_off", _i), ("aux", _vp), ("ldaux", _i), ("splitk_scratch", _vp), ("splitk_scratch_bytes", C.c_size_t),
+                ("colsum", _vp)]
 
 
 # symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/fact_sm100.h
@@ -96,6 +100,9 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
+    if lib.fact_abi_version() != ABI_VERSION:
+        raise FactError(f"{LIB_PATH} has ABI version {lib.fact_abi_version()}, this package needs {ABI_VERSION}: "
+                        "rebuild with `python -m mint_b200.build --force`")
     from . import lib_bwd  # optional training symbols (same .so)
     lib_bwd.bind(lib)
     # developer aid: FACT_FLAGS="gemm_tma_store=0,gemm_pair=1" -> fact_set_flag for A/B timing of kernel variants

@@ -1,0 +1,14 @@
+#!/bin/bash
+set -u
+out=gpurun_out/exp_wgrad
+mkdir -p $out
+timeout 600 python -m pytest tests/test_backward_gpu.py -x -q -m gpu -k "wgrad" > $out/pytest.log 2>&1
+tail -4 $out/pytest.log
+for f in 0 1; do
+  echo "== wgrad_pair=$f"
+  FACT_FLAGS=wgrad_pair=$f timeout 300 python scripts/bench_train.py --steps 4 --warmup 2 2>/dev/null | tail -1 | python -c "import json,sys; r=json.loads(sys.stdin.read()); print(r['ms_per_step'], r['loss_last'])"
+done
+timeout 600 python -m pytest tests/test_train_gpu.py tests/test_backward_gpu.py -x -q -m gpu > $out/pytest_train.log 2>&1
+tail -3 $out/pytest_train.log
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:wgrad -c 140 --csv --log-file $out/launches_wgrad.csv python scripts/bench_train.py --steps 1 --warmup 1 > $out/ncu.log 2>&1
+python scripts/summarize_launches.py $out/launches_wgrad.csv | head -5

@@ -29,6 +29,32 @@ def test_wgrad_gemm(fact_lib, cuda, tokens, in_dim, out_dim):
     assert rel_err(dw, ref) < 2e-5, rel_err(dw, ref)
 
 
+@pytest.mark.parametrize("tokens,in_dim,out_dim", [(4608, 800, 2400), (5000, 3072, 800), (4100, 304, 520),
+                                                    (4096, 256, 256), (9001, 800, 3072), (12000, 800, 800)])
+def test_wgrad_gemm_pair(fact_lib, cuda, tokens, in_dim, out_dim):
+    """Problems large enough for the CTA-pair kernel (256 x 256 tiles, bulk fp32 reductions into dW): partial tiles on
+    both matrix edges, a token count that is not a multiple of the 64-token block, accumulation on top of dW, nothing
+    written outside [in, out]; and the 1-SM kernel (flag off) agrees."""
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(tokens, in_dim, generator=g).to(cuda).to(BF)
+    dy = torch.randn(tokens, out_dim, generator=g).to(cuda).to(BF)
+    ref = x.double().t() @ dy.double() + 0.5
+    outs = []
+    for flag in (1, 0):
+        fact_lib.fact_set_flag(b"wgrad_pair", flag)
+        buf = torch.full((in_dim + 8, out_dim), 0.5, device=cuda)     # 8 guard rows behind the gradient
+        try:
+            L.check(fact_lib.fact_wgrad_gemm(x.data_ptr(), in_dim, dy.data_ptr(), out_dim, buf.data_ptr(), out_dim,
+                                             tokens, in_dim, out_dim, _st()), "fact_wgrad_gemm")
+            torch.cuda.synchronize()
+        finally:
+            fact_lib.fact_set_flag(b"wgrad_pair", 1)
+        assert (buf[in_dim:] == 0.5).all(), f"flag {flag}: wrote past row {in_dim}"
+        assert rel_err(buf[:in_dim], ref) < 2e-5, (flag, rel_err(buf[:in_dim], ref))
+        outs.append(buf[:in_dim].clone())
+    assert rel_err(outs[0], outs[1].double()) < 1e-5
+
+
 def test_wgrad_gemm_padded_operand(fact_lib, cuda):
     """dy with a padded pitch (the head's 225 -> 256 columns) and a gradient narrower than the pitch."""
     tokens, in_dim, out_dim, ldy = 500, 800, 225, 256

@@ -203,11 +203,17 @@ def test_gemm_pair_tma_store_bitwise(fact_lib, cuda, m, n, k, kind, precise):
                 e.scale, e.scale_cols = 0.37, n // 3
                 e.aux, e.ldaux = z.data_ptr(), n
                 outs = (o_hi, o_lo)
+                if kind == L.EPI_GELU_GRAD:    # bias gradient folded into the epilogue (or a second pass: flag 0)
+                    colsum = torch.zeros(n, device=cuda)
+                    e.colsum = colsum.data_ptr()
             L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, k, w_hi.data_ptr(),
                                        w_lo.data_ptr() if precise else None, k, m, n, k, C.byref(e), _st()))
             torch.cuda.synchronize()
             for o in outs:
                 assert (o[m:].float() == 7.0).all(), f"flag {flag}: wrote past row {m}"
+            if kind == L.EPI_GELU_GRAD:
+                ref_cs = o_hi[:m].double().sum(0)
+                assert (colsum.double() - ref_cs).abs().max() < 1e-4 * (1.0 + ref_cs.abs().max()), flag
             results.append([o.clone() for o in outs])
     finally:
         fact_lib.fact_set_flag(b"gemm_pair", 1)
