@@ -679,6 +679,9 @@ int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float*
   return FACT_OK;
 }
 
+int sdpa_bwd_tc_try(const bf16* qkv, const bf16* d_o, const float* lse, const float* Dv, bf16* dqkv, float* dq_acc,
+                    int batch, int n, int heads, int head_dim, float k_scale, cudaStream_t st, bool* done);  // sdpa_bwd_tc.cu
+
 int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* Dv, float* dq_acc,
                   void* dqkv, int batch, int n, int heads, int head_dim, float scale, cudaStream_t st) {
   FACT_REQUIRE(qkv && o && d_o && lse && Dv && dq_acc && dqkv, FACT_ERR_BAD_SHAPE, "sdpa_backward: null buffer");
@@ -695,6 +698,12 @@ int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* 
   }
   dim3 grid((n + 63) / 64, heads, batch);
   const float k_scale = 0.6931471805599453f;  // dK = ln2 * dZ^T q'   (q' = q * scale * log2 e)
+  bool tc_done = false;  // FACT shapes: the tcgen05 kernel
+  {
+    const int rc = sdpa_bwd_tc_try(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_o), lse, Dv,
+                                   static_cast<bf16*>(dqkv), dq_acc, batch, n, heads, head_dim, k_scale, st, &tc_done);
+    if (rc != FACT_OK) return rc;
+  }
 #define FACT_BWD_CASE(DHV)                                                                                         \
   case DHV: {                                                                                                      \
     constexpr int smem = (6 * 64 * (DHV + 8) + 64 * 72) * 2 + 4 * 64 * 4;                                          \
@@ -707,14 +716,16 @@ int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* 
                                                   Dv, static_cast<bf16*>(dqkv), dq_acc, n, heads, k_scale);        \
     break;                                                                                                         \
   }
-  switch (head_dim) {
-    FACT_BWD_CASE(16)
-    FACT_BWD_CASE(32)
-    FACT_BWD_CASE(64)
-    FACT_BWD_CASE(80)
+  if (!tc_done) {
+    switch (head_dim) {
+      FACT_BWD_CASE(16)
+      FACT_BWD_CASE(32)
+      FACT_BWD_CASE(64)
+      FACT_BWD_CASE(80)
+    }
+    FACT_LAUNCH_CHECK("sdpa_bwd_kernel");
   }
 #undef FACT_BWD_CASE
-  FACT_LAUNCH_CHECK("sdpa_bwd_kernel");
   long long total = tokens * (d / 4);
   int g2 = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   sdpa_bwd_finish_kernel<<<g2, 256, 0, st>>>(dq_acc, static_cast<bf16*>(dqkv), tokens, d, scale);

@@ -38,6 +38,8 @@ int cuda_fail(cudaError_t e, const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols);
 // fp32 / bf16 row-major output matrix -> {32, 32} box map for bulk tensor stores / reductions (gemm_tc.cu)
 int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes);
+int make_tmap_box(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes, int box_rows,
+                  int box_cols);
 int num_sms();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

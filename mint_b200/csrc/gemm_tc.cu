@@ -968,11 +968,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
   return FACT_OK;
 }
 
-// Output side of the TMA-store epilogue: row-major [rows, cols] of bf16 (elem_bytes 2) or fp32 (4), box 32 x 32,
-// swizzle span = the box's row bytes (64 / 128) so the row-per-lane staging writes are bank-conflict free.
-int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes) {
+// Row-major [rows, cols] matrix of bf16 (elem_bytes 2) or fp32 (4) -> map with a {box_cols, box_rows} box whose swizzle
+// span equals the box's row bytes (32 / 64 / 128), the layout the staging writes of the bulk-store epilogues assume.
+int make_tmap_box(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes, int box_rows,
+                  int box_cols) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, rows, cols, ld, 32, elem_bytes};
+  TmapKey key{ptr, rows, cols, ld, box_rows, box_cols * 8 + elem_bytes};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -980,19 +981,28 @@ int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld,
   }
   EncodeTiledFn enc = get_encode_fn();
   FACT_REQUIRE(enc != nullptr, FACT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int span = box_cols * elem_bytes;
+  FACT_REQUIRE(span == 32 || span == 64 || span == 128, FACT_ERR_UNSUPPORTED, "tensor-map box row of %d bytes", span);
+  FACT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (static_cast<long long>(ld) * elem_bytes) % 16 == 0,
+               FACT_ERR_BAD_ALIGN, "bulk tensor store needs a 16-byte aligned base and row pitch");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = span == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FACT_REQUIRE(r == CUDA_SUCCESS, FACT_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d) rows=%d cols=%d ld=%d",
                static_cast<int>(r), rows, cols, ld);
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, *out);
   return FACT_OK;
+}
+// the 32 x 32 box of the GEMM epilogues
+int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes) {
+  return make_tmap_box(out, ptr, rows, cols, ld, elem_bytes, 32, 32);
 }
 
 int num_sms() {

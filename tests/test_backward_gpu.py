@@ -93,7 +93,7 @@ def test_gelu_save_and_grad_epilogues(fact_lib, cuda):
 
 @pytest.mark.parametrize("legacy", [0, 1])
 @pytest.mark.parametrize("batch,n,heads,dh", [(2, 120, 10, 80), (1, 360, 10, 80), (2, 37, 2, 16), (1, 130, 3, 64),
-                                              (3, 240, 4, 80)])
+                                              (3, 240, 4, 80), (3, 360, 10, 80), (5, 200, 2, 80), (2, 384, 1, 80)])
 def test_sdpa_forward_lse_and_backward(fact_lib, cuda, batch, n, heads, dh, legacy):
     if legacy and dh != 80:
         pytest.skip("already the mma.sync path")
@@ -128,14 +128,21 @@ def test_sdpa_forward_lse_and_backward(fact_lib, cuda, batch, n, heads, dh, lega
     d_o = torch.randn(batch * n, d, generator=g).to(cuda).to(BF)
     out.backward(d_o.double())
     dref = torch.stack([t.grad.permute(0, 2, 1, 3).reshape(batch * n, d) for t in (q, k, v)], 1).reshape(batch * n, 3 * d)
-    dqkv = torch.zeros(batch * n, 3 * d, device=cuda, dtype=BF)
-    dscr = torch.zeros(batch * heads * n, device=cuda)
-    dq_scr = torch.zeros(batch * n * d, device=cuda)
-    L.check(fact_lib.fact_sdpa_backward(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dscr.data_ptr(),
-                                        dq_scr.data_ptr(), dqkv.data_ptr(), batch, n, heads, dh, scale, _st()))
-    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
-        err = rel_err(dqkv[:, sl].float(), dref[:, sl])
-        assert err < 3e-2, (name, err)
+    for bwd_tc in ((1, 0) if dh == 80 else (1,)):              # tcgen05 kernel, then the mma.sync kernel
+        dqkv = torch.zeros(batch * n, 3 * d, device=cuda, dtype=BF)
+        dscr = torch.zeros(batch * heads * n, device=cuda)
+        dq_scr = torch.zeros(batch * n * d, device=cuda)
+        fact_lib.fact_set_flag(b"sdpa_bwd_tc", bwd_tc)
+        try:
+            L.check(fact_lib.fact_sdpa_backward(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                                dscr.data_ptr(), dq_scr.data_ptr(), dqkv.data_ptr(), batch, n, heads,
+                                                dh, scale, _st()))
+            torch.cuda.synchronize()
+        finally:
+            fact_lib.fact_set_flag(b"sdpa_bwd_tc", 1)
+        for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+            err = rel_err(dqkv[:, sl].float(), dref[:, sl])
+            assert err < 3e-2, (name, err, bwd_tc)
 
 
 @pytest.mark.parametrize("rows,d", [(37, 800), (1000, 800), (64, 64)])
