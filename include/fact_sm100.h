@@ -129,6 +129,11 @@ typedef struct fact_grads {
  * lo may be NULL. */
 FACT_API int fact_pack_weight(const float* w_keras, void* hi, void* lo, int k_in, int n_out, void* stream);
 
+/* The same for `count` kernels in ONE launch (arrays of host pointers / sizes; lo may be NULL, or hold NULL entries):
+ * what the training step calls after every optimizer update. */
+FACT_API int fact_pack_weights(const float* const* w_keras, void* const* hi, void* const* lo, const int* k_in,
+                               const int* n_out, int count, void* stream);
+
 /* ---- building-block kernels (each is also a unit-test seam) ---------------------------------------------- */
 
 /* Norm: y = LayerNorm(x; gamma, beta, eps=1e-5) (base_models.py:27-31), written as bf16 hi (+lo).
@@ -264,9 +269,10 @@ FACT_API int fact_cast_colsum(const float* x, int ldx, void* y_bf16, int ldy, fl
 FACT_API int fact_cast_weight(const float* w_keras, void* out_bf16, int rows, int cols, int ld_out, void* stream);
 
 /* Keras Adam (trainer.py:150; beta1 .9, beta2 .999, epsilon 1e-7 outside the root) on a flat range;
- * g is multiplied by grad_scale first (global-norm clipping). step counts from 1. */
+ * g is multiplied by grad_scale first (global-norm clipping). step counts from 1.  w_bf16 (optional, n elements): also
+ * receives bf16(w) -- the Keras-layout operand copies of the backward GEMMs, refreshed without another pass. */
 FACT_API int fact_adam_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                            float beta2, float eps, long long step, float grad_scale, void* stream);
+                            float beta2, float eps, long long step, float grad_scale, void* w_bf16, void* stream);
 
 /* *out = sum g^2 (for clip_by_global_norm, single_task_trainer.py:180-183). */
 FACT_API int fact_sum_squares(const float* g, long long n, float* out, void* stream);

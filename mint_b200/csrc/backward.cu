@@ -361,42 +361,53 @@ __global__ void __launch_bounds__(256) sdpa_bwd_finish_kernel(const float* __res
 }
 
 // =========================================================================================== LayerNorm backward
-// One launch, two phases per 32-row slab (HBM sees x, dy and dres once: the second phase re-reads x / dy from L1 / L2):
-//  (1) one warp per row: stats[row] = {mean, rstd, mean(g*dy), rstd * mean(g*dy*xhat)} into shared memory
+// One launch; each block owns a slab of 16 rows.  The slab's x and dy rows (contiguous in memory) arrive in shared
+// memory through two bulk async copies, so HBM sees x, dy and dres exactly once and no registers are tied up by loads in
+// flight (two blocks per SM: one slab streams in while the other computes).
+//  (1) one warp per row: stats[row] = {mean, rstd, mean(g*dy), rstd * mean(g*dy*xhat)}
 //  (2) thread = one float4 column group: dx = dres + rstd*(g*dy - m1 - xhat*m2); dgamma / dbeta (and, optionally, the
-//      column sums of dx = the bias gradient of the dense layer that produced x's residual branch) stay in registers
-//      and leave through one atomicAdd per column per block; dx is optionally also written as the bf16 GEMM operand.
-// (A one-pass register-resident version needed 154 registers -> 8 warps/SM and ran at a quarter of HBM speed.)
-constexpr int LN_ROWS_PER_BLOCK = 32;
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ dy, const float* dres, float* dx,
-                                                     bf16* __restrict__ dx_b, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, float* __restrict__ colsum, int rows,
-                                                     int d) {
-  __shared__ float4 sstats[LN_ROWS_PER_BLOCK];
+//      column sums of dx = the bias gradient of the dense layer feeding this residual branch) stay in registers and
+//      leave through one atomicAdd per column per block; dx is optionally also written as the bf16 GEMM operand.
+// (A register-resident one-pass version needed 154 registers and ran at a quarter of HBM speed; a two-kernel version
+// read x and dy twice.)
+constexpr int LN_ROWS_PER_BLOCK = 16;
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ dy, const float* dres, float* dx,
+                                                        bf16* __restrict__ dx_b, float* __restrict__ dgamma,
+                                                        float* __restrict__ dbeta, float* __restrict__ colsum,
+                                                        int rows, int d) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  float* xs = reinterpret_cast<float*>(ln_smem);                    // [16][d]
+  float* ys = xs + LN_ROWS_PER_BLOCK * d;                           // [16][d]
+  float4* sstats = reinterpret_cast<float4*>(ys + LN_ROWS_PER_BLOCK * d);
+  const uint32_t bar = smem_u32(sstats + LN_ROWS_PER_BLOCK);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = d >> 2;
   const int r0 = blockIdx.x * LN_ROWS_PER_BLOCK;
-  const int r1 = min(rows, r0 + LN_ROWS_PER_BLOCK);
+  const int nr = min(rows - r0, LN_ROWS_PER_BLOCK);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    const uint32_t bytes = static_cast<uint32_t>(nr) * d * 4;
+    mbar_arrive_expect_tx(bar, 2 * bytes);
+    bulk_load_1d(smem_u32(xs), x + static_cast<size_t>(r0) * d, bytes, bar);
+    bulk_load_1d(smem_u32(ys), dy + static_cast<size_t>(r0) * d, bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   // ---- phase 1
-  for (int row = r0 + warp; row < r1; row += 8) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
-    const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * d);
-    float4 v[8], u[8];
+  for (int rl = warp; rl < nr; rl += 8) {
+    const float4* xr = reinterpret_cast<const float4*>(xs + rl * d);
+    const float4* yr = reinterpret_cast<const float4*>(ys + rl * d);
+    float4 v[8];
+    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = lane + i * 32;
       v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = lane + i * 32;
-      u[i] = idx < nv ? yr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / d;
@@ -416,7 +427,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
       const int idx = lane + i * 32;
       if (idx < nv) {
         const float4 gg = __ldg(g4 + idx);
-        const float a0 = gg.x * u[i].x, a1 = gg.y * u[i].y, a2 = gg.z * u[i].z, a3 = gg.w * u[i].w;
+        const float4 u = yr[idx];
+        const float a0 = gg.x * u.x, a1 = gg.y * u.y, a2 = gg.z * u.z, a3 = gg.w * u.w;
         s1 += (a0 + a1) + (a2 + a3);
         s2 += (a0 * v[i].x + a1 * v[i].y) + (a2 * v[i].z + a3 * v[i].w);
       }
@@ -426,7 +438,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0) sstats[row - r0] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
+    if (lane == 0) sstats[rl] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
   }
   __syncthreads();
   // ---- phase 2
@@ -435,11 +447,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
   const float4 gg = __ldg(g4 + cg);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
 #pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    const size_t off = static_cast<size_t>(r) * nv + cg;
-    const float4 xv = reinterpret_cast<const float4*>(x)[off];
-    const float4 dyv = reinterpret_cast<const float4*>(dy)[off];
-    const float4 st = sstats[r - r0];  // mean, rstd, m1, m2
+  for (int rl = 0; rl < nr; ++rl) {
+    const size_t off = static_cast<size_t>(r0 + rl) * nv + cg;
+    const float4 xv = reinterpret_cast<const float4*>(xs + rl * d)[cg];
+    const float4 dyv = reinterpret_cast<const float4*>(ys + rl * d)[cg];
+    const float4 st = sstats[rl];  // mean, rstd, m1, m2
     float4 xh;
     xh.x = (xv.x - st.x) * st.y; xh.y = (xv.y - st.x) * st.y; xh.z = (xv.z - st.x) * st.y; xh.w = (xv.w - st.x) * st.y;
     float4 o;
@@ -604,14 +616,17 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
 // w -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)      (eps = 1e-7 outside the root)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
-                                                   float lr_t, float b1, float b2, float eps, float grad_scale) {
+                                                   float lr_t, float b1, float b2, float eps, float grad_scale,
+                                                   bf16* __restrict__ w_bf16) {
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    const float wi = w[i] - lr_t * mi / (sqrtf(vi) + eps);
+    w[i] = wi;
+    if (w_bf16) w_bf16[i] = __float2bfloat16_rn(wi);
   }
 }
 
@@ -739,7 +754,15 @@ int ln_backward(const float* x, const float* gamma, const float* dy, const float
                 float* dgamma, float* dbeta, float* colsum, int rows, int d, cudaStream_t st) {
   FACT_REQUIRE(d % 4 == 0 && d <= 1024, FACT_ERR_BAD_SHAPE, "ln_backward: d %d", d);
   FACT_REQUIRE(dy != dx, FACT_ERR_BAD_SHAPE, "ln_backward: dx must not alias dy (it may alias dres)");
-  ln_bwd_kernel<<<(rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK, 256, 0, st>>>(
+  FACT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, FACT_ERR_BAD_ALIGN,
+               "ln_backward: x and dy must be 16-byte aligned");
+  const int smem = 2 * LN_ROWS_PER_BLOCK * d * 4 + LN_ROWS_PER_BLOCK * 16 + 16;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  ln_bwd_kernel<<<(rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK, 256, smem, st>>>(
       x, gamma, dy, dres, dx, static_cast<bf16*>(dx_b), dgamma, dbeta, colsum, rows, d);
   FACT_LAUNCH_CHECK("ln_bwd_kernel");
   return FACT_OK;
@@ -844,14 +867,15 @@ extern "C" int fact_cast_colsum(const float* x, int ldx, void* y_bf16, int ldy, 
 }
 
 extern "C" int fact_adam_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                              float beta2, float eps, long long step, float grad_scale, void* stream) {
+                              float beta2, float eps, long long step, float grad_scale, void* w_bf16, void* stream) {
   FACT_REQUIRE(w && g && m && v && n > 0 && step >= 1, FACT_ERR_BAD_SHAPE, "fact_adam_step: bad arguments");
   const double t = static_cast<double>(step);
   const float lr_t = static_cast<float>(lr * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
                                         (1.0 - pow(static_cast<double>(beta1), t)));
   long long blocks = (n + 255) / 256;
   int grid = static_cast<int>(blocks > 16384 ? 16384 : blocks);
-  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale,
+                                                   static_cast<bf16*>(w_bf16));
   FACT_LAUNCH_CHECK("adam_kernel");
   return FACT_OK;
 }

@@ -111,6 +111,43 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
   }
 }
 
+// every dense kernel of the model in one launch (the training step repacks all of them after the optimizer update)
+constexpr int PACK_MAX = 80;
+struct PackTable {
+  const float* w[PACK_MAX];
+  bf16* hi[PACK_MAX];
+  bf16* lo[PACK_MAX];
+  int k_in[PACK_MAX], n_out[PACK_MAX];
+  int tile0[PACK_MAX + 1];  // first 32 x 32 tile of tensor i in the flat grid
+  int count;
+};
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackTable t) {
+  __shared__ float tile[32][33];
+  int idx = 0;
+  while (idx + 1 < t.count && static_cast<int>(blockIdx.x) >= t.tile0[idx + 1]) ++idx;
+  const int k_in = t.k_in[idx], n_out = t.n_out[idx];
+  const int local = blockIdx.x - t.tile0[idx], tiles_n = (n_out + 31) / 32;
+  const int k0 = (local / tiles_n) * 32, n0 = (local % tiles_n) * 32;
+  const float* __restrict__ w = t.w[idx];
+  bf16* __restrict__ hi = t.hi[idx];
+  bf16* __restrict__ lo = t.lo[idx];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < k_in && n < n_out) ? w[static_cast<size_t>(k) * n_out + n] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (n < n_out && k < k_in) {
+      bf16 h, l;
+      split_bf16(tile[tx][r], h, l);
+      hi[static_cast<size_t>(n) * k_in + k] = h;
+      if (lo) lo[static_cast<size_t>(n) * k_in + k] = l;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- fp32 SIMT GEMM
 struct SimtArgs {
   // A operand: either fp32 (a_f32) or split bf16 (a_hi [+ a_lo]); row r lives at
@@ -419,6 +456,32 @@ extern "C" int fact_pack_weight(const float* w_keras, void* hi, void* lo, int k_
   pack_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_keras, static_cast<bf16*>(hi), static_cast<bf16*>(lo),
                                                           k_in, n_out);
   FACT_LAUNCH_CHECK("pack_weight_kernel launch");
+  return FACT_OK;
+}
+
+extern "C" int fact_pack_weights(const float* const* w_keras, void* const* hi, void* const* lo, const int* k_in,
+                                 const int* n_out, int count, void* stream) {
+  FACT_REQUIRE(w_keras && hi && k_in && n_out && count > 0, FACT_ERR_BAD_SHAPE, "fact_pack_weights: bad arguments");
+  for (int base = 0; base < count; base += PACK_MAX) {
+    PackTable t{};
+    t.count = count - base < PACK_MAX ? count - base : PACK_MAX;
+    int tiles = 0;
+    for (int i = 0; i < t.count; ++i) {
+      const int j = base + i;
+      FACT_REQUIRE(w_keras[j] && hi[j] && k_in[j] > 0 && n_out[j] > 0, FACT_ERR_BAD_SHAPE,
+                   "fact_pack_weights: bad entry %d", j);
+      t.w[i] = w_keras[j];
+      t.hi[i] = static_cast<bf16*>(hi[j]);
+      t.lo[i] = lo ? static_cast<bf16*>(lo[j]) : nullptr;
+      t.k_in[i] = k_in[j];
+      t.n_out[i] = n_out[j];
+      t.tile0[i] = tiles;
+      tiles += ((k_in[j] + 31) / 32) * ((n_out[j] + 31) / 32);
+    }
+    t.tile0[t.count] = tiles;
+    pack_weights_kernel<<<tiles, 256, 0, as_stream(stream)>>>(t);
+    FACT_LAUNCH_CHECK("pack_weights_kernel launch");
+  }
   return FACT_OK;
 }
 

@@ -50,6 +50,8 @@ class FACTModel:
         self._grad_flat: torch.Tensor | None = None
         self._packed: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}
         self._keras_bf16: dict[str, torch.Tensor] = {}  # Keras-layout bf16 copies (backward dX GEMMs), training only
+        self._kl_flat: torch.Tensor | None = None       # ... which are views into this bf16 mirror of the bucket
+        self._kl_end = 0
         self._train_ws: torch.Tensor | None = None
         self._ws: dict[tuple, torch.Tensor] = {}
         self._side_stream = None
@@ -84,7 +86,7 @@ class FACTModel:
                 for v in shp:
                     n *= v
                 self._offsets[name] = (off, n)
-                off += (n + 3) // 4 * 4                      # keep every tensor 16-byte aligned inside the bucket
+                off += (n + 7) // 8 * 8                      # every tensor 16-byte aligned, also in the bf16 copy
             self._flat = torch.zeros(off, dtype=torch.float32, device=self.device)
             for name, shp in shapes.items():
                 o, n = self._offsets[name]
@@ -96,25 +98,41 @@ class FACTModel:
             self._params[name].copy_(t.to(self.device))
         self.repack()
 
-    def repack(self) -> None:
-        """(Re)build the K-major bf16 hi/lo copies the tensor-core GEMMs read (after any weight update)."""
+    def repack(self, bf16_copy_done: bool = False) -> None:
+        """(Re)build the bf16 operand copies the tensor-core GEMMs read (after any weight update): the K-major hi/lo
+        (transposed) copies in ONE launch, and, in training, the Keras-layout bf16 copy of the whole bucket (skipped
+        when the optimizer kernel has just written it)."""
         st = torch.cuda.current_stream(self.device).cuda_stream
+        names = [n for n in self._params if n.endswith("/kernel") and "linear_embedding" not in n]
+        precise = self.mode != "bf16"
+        for name in names:
+            if name not in self._packed:
+                k_in, n_out = self._params[name].shape
+                hi = torch.empty((n_out, k_in), dtype=_TORCH_BF16, device=self.device)
+                self._packed[name] = (hi, torch.empty_like(hi) if precise else None)
+        cnt = len(names)
+        vp = C.c_void_p * cnt
+        w_arr = vp(*[self._params[n].data_ptr() for n in names])
+        hi_arr = vp(*[self._packed[n][0].data_ptr() for n in names])
+        lo_arr = vp(*[self._packed[n][1].data_ptr() if precise else None for n in names])
+        k_arr = (C.c_int * cnt)(*[self._params[n].shape[0] for n in names])
+        n_arr = (C.c_int * cnt)(*[self._params[n].shape[1] for n in names])
         with torch.cuda.device(self.device):
-            for name, p in self._params.items():
-                if not name.endswith("/kernel") or "linear_embedding" in name:
-                    continue
-                k_in, n_out = p.shape
-                if name not in self._packed:
-                    self._packed[name] = (torch.empty((n_out, k_in), dtype=_TORCH_BF16, device=self.device),
-                                          torch.empty((n_out, k_in), dtype=_TORCH_BF16, device=self.device))
-                hi, lo = self._packed[name]
-                lib.check(self._lib.fact_pack_weight(p.data_ptr(), hi.data_ptr(), lo.data_ptr(), k_in, n_out, st),
-                          "fact_pack_weight")
-                if name in self._keras_bf16:
-                    kl = self._keras_bf16[name]
-                    lib.check(self._lib.fact_cast_weight(p.data_ptr(), kl.data_ptr(), k_in, n_out, kl.shape[1], st),
-                              "fact_cast_weight")
+            lib.check(self._lib.fact_pack_weights(w_arr, hi_arr, lo_arr, k_arr, n_arr, cnt, st), "fact_pack_weights")
+            if self._kl_flat is not None:
+                if not bf16_copy_done:
+                    self._kl_flat.copy_(self._flat)              # round-to-nearest, as the optimizer kernel does
+                for name, kl in self._keras_bf16.items():        # padded copies (the head: 225 -> 256 columns)
+                    if kl.data_ptr() < self._kl_flat.data_ptr() or kl.data_ptr() >= self._kl_end:
+                        p = self._params[name]
+                        lib.check(self._lib.fact_cast_weight(p.data_ptr(), kl.data_ptr(), p.shape[0], p.shape[1],
+                                                             kl.shape[1], st), "fact_cast_weight")
         self._build_tables()
+
+    @property
+    def flat_bf16_parameters(self):
+        """bf16 mirror of flat_parameters (training only; None before the first training call)."""
+        return self._kl_flat
 
     def _build_tables(self) -> None:
         P, K = self._params, self._packed
@@ -284,11 +302,17 @@ class FACTModel:
             o, n = self._offsets[name]
             self._grads[name] = self._grad_flat[o:o + n].view(p.shape)
         pad64 = lambda v: (v + 63) // 64 * 64
+        self._kl_flat = torch.zeros(self._flat.numel(), dtype=_TORCH_BF16, device=self.device)
+        self._kl_end = self._kl_flat.data_ptr() + 2 * self._kl_flat.numel()
         for name, p in self._params.items():
             if name.endswith("/kernel") and "linear_embedding" not in name:
                 cols = p.shape[1]
-                ld = pad64(cols) if name == "cross_modal_layer/output/kernel" else cols
-                self._keras_bf16[name] = torch.zeros((p.shape[0], ld), dtype=_TORCH_BF16, device=self.device)
+                if name == "cross_modal_layer/output/kernel":    # 16-byte row pitch for TMA: own padded buffer
+                    self._keras_bf16[name] = torch.zeros((p.shape[0], pad64(cols)), dtype=_TORCH_BF16,
+                                                         device=self.device)
+                else:
+                    o, n = self._offsets[name]
+                    self._keras_bf16[name] = self._kl_flat[o:o + n].view(p.shape)
         self.repack()
         self._build_grad_tables()
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "fact_last_error": (C.c_char_p, []),
     "fact_launch_count": (C.c_longlong, []),
     "fact_pack_weight": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "fact_pack_weights": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp]),
     "fact_layernorm_split": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "fact_gemm": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp]),
     "fact_gemm_f32": (_i, [_vp, _i, _vp, _i, _i, _i, C.POINTER(GemmEpilogue), _vp]),

@@ -13,7 +13,7 @@ SIGNATURES: dict = {
     "fact_embed_backward": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fact_cast_colsum": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     "fact_cast_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "fact_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _ll, _f, _vp]),
+    "fact_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _ll, _f, _vp, _vp]),
     "fact_sum_squares": (_i, [_vp, _ll, _vp, _vp]),
     "fact_train_workspace_bytes": (C.c_size_t, [_vp, _i]),
     "fact_train_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, C.c_size_t, _vp]),

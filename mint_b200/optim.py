@@ -80,10 +80,12 @@ class Adam:
         self.iterations += 1
         with torch.cuda.device(model.device):
             st = torch.cuda.current_stream(model.device).cuda_stream
+            kl = model.flat_bf16_parameters      # bf16 copy of the bucket (Keras-layout operands of the dX GEMMs)
             lib.check(self._lib.fact_adam_step(flat.data_ptr(), grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                                flat.numel(), lr, self.beta_1, self.beta_2, self.epsilon,
-                                               self.iterations, float(grad_scale), st), "fact_adam_step")
-        model.repack()
+                                               self.iterations, float(grad_scale),
+                                               kl.data_ptr() if kl is not None else None, st), "fact_adam_step")
+        model.repack(bf16_copy_done=kl is not None)
 
     def state_dict(self):
         return {"iterations": self.iterations, "m": self.m, "v": self.v}

@@ -3,7 +3,7 @@
 set -u
 out=gpurun_out/exp_train
 mkdir -p $out
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_backward_gpu.py tests/test_train_gpu.py -x -q -m gpu > $out/pytest.log 2>&1
+timeout 1200 python -m pytest tests -x -q -m gpu > $out/pytest.log 2>&1
 tail -5 $out/pytest.log
 timeout 300 python scripts/bench_train.py --steps 4 --warmup 2 2>/dev/null | tail -1
 if [ "${1:-}" = "ncu" ]; then

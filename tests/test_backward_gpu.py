@@ -202,15 +202,17 @@ def test_adam_matches_keras_formula(fact_lib, cuda):
     vv = torch.zeros_like(mm)
     lr, b1, b2, eps = 1e-4, 0.9, 0.999, 1e-7
     ref = w0.clone()
+    w_b = torch.zeros(n, device=cuda, dtype=BF)
     for step in (1, 2, 3):
         L.check(fact_lib.fact_adam_step(w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps,
-                                        step, 0.5, _st()))
+                                        step, 0.5, w_b.data_ptr() if step > 1 else None, _st()))
         gd = g.double() * 0.5
         mm = b1 * mm + (1 - b1) * gd
         vv = b2 * vv + (1 - b2) * gd * gd
         lr_t = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
         ref = ref - lr_t * mm / (vv.sqrt() + eps)
     assert (w.double() - ref).abs().max() < 1e-6
+    assert torch.equal(w_b, w.to(BF))                          # the bf16 operand copy written by the same pass
     ss = torch.zeros((), device=cuda)
     L.check(fact_lib.fact_sum_squares(g.data_ptr(), n, ss.data_ptr(), _st()))
     assert abs(float(ss) - float((g.double() ** 2).sum())) < 1e-3 * float((g.double() ** 2).sum())
