@@ -172,6 +172,9 @@ typedef struct fact_gemm_epilogue {
   /* FACT_EPI_GELU_GRAD, optional: colsum[c] += sum over rows of the bf16 output (the bias gradient of the FFN hidden
    * layer) -- folded into the epilogue instead of a second pass over the [m, n] output.  fp32 [n], NULL = skip. */
   float* colsum;
+  /* FACT_EPI_BIAS_RESID_F32, optional: > 0 makes resid a [resid_rows, ldr] table read at row % resid_rows (the
+   * position embedding added to every clip, base_models.py:148-156); 0 = resid has one row per output row. */
+  int resid_rows;
 } fact_gemm_epilogue;
 
 /* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).

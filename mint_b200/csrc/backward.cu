@@ -361,114 +361,135 @@ __global__ void __launch_bounds__(256) sdpa_bwd_finish_kernel(const float* __res
 }
 
 // =========================================================================================== LayerNorm backward
-// One launch; each block owns a slab of 16 rows.  The slab's x and dy rows (contiguous in memory) arrive in shared
-// memory through two bulk async copies, so HBM sees x, dy and dres exactly once and no registers are tied up by loads in
-// flight (two blocks per SM: one slab streams in while the other computes).
+// One persistent launch (a block per SM).  Rows are processed in 8-row slabs; a slab's x and dy rows (contiguous in
+// memory, like dres) arrive in shared memory through bulk async copies into a two-deep ring, so HBM sees x, dy and
+// dres exactly once, the next slab is in flight while the current one is processed, and the compute phases never wait
+// on a global load (ncu on the non-pipelined version: 20 % of the warp slots active, 50 % of the HBM peak, all stalls
+// on loads; with dres still read directly in phase 2 the slab time was two global round trips).
 //  (1) one warp per row: stats[row] = {mean, rstd, mean(g*dy), rstd * mean(g*dy*xhat)}
 //  (2) thread = one float4 column group: dx = dres + rstd*(g*dy - m1 - xhat*m2); dgamma / dbeta (and, optionally, the
-//      column sums of dx = the bias gradient of the dense layer feeding this residual branch) stay in registers and
-//      leave through one atomicAdd per column per block; dx is optionally also written as the bf16 GEMM operand.
-// (A register-resident one-pass version needed 154 registers and ran at a quarter of HBM speed; a two-kernel version
-// read x and dy twice.)
-constexpr int LN_ROWS_PER_BLOCK = 16;
-__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+//      column sums of dx = the bias gradient of the dense layer feeding this residual branch) stay in registers over
+//      ALL the block's slabs and leave through one atomicAdd per column per block; dx is optionally also written as
+//      the bf16 GEMM operand.
+constexpr int LN_SLAB = 8;
+__global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ dy, const float* dres, float* dx,
                                                         bf16* __restrict__ dx_b, float* __restrict__ dgamma,
                                                         float* __restrict__ dbeta, float* __restrict__ colsum,
-                                                        int rows, int d) {
+                                                        int rows, int d, int stages) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
-  float* xs = reinterpret_cast<float*>(ln_smem);                    // [16][d]
-  float* ys = xs + LN_ROWS_PER_BLOCK * d;                           // [16][d]
-  float4* sstats = reinterpret_cast<float4*>(ys + LN_ROWS_PER_BLOCK * d);
-  const uint32_t bar = smem_u32(sstats + LN_ROWS_PER_BLOCK);
+  const int slab_floats = LN_SLAB * d;                               // one array of one slab
+  float* ring = reinterpret_cast<float*>(ln_smem);                   // [stages][3][LN_SLAB][d]: x, dy, dres
+  float4* sstats = reinterpret_cast<float4*>(ring + static_cast<size_t>(stages) * 3 * slab_floats);
+  const uint32_t bar0 = smem_u32(sstats + LN_SLAB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = d >> 2;
-  const int r0 = blockIdx.x * LN_ROWS_PER_BLOCK;
-  const int nr = min(rows - r0, LN_ROWS_PER_BLOCK);
+  const int num_slabs = (rows + LN_SLAB - 1) / LN_SLAB;
+  const int my_slabs = blockIdx.x < num_slabs ? (num_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](int j) {  // thread 0: slab j of this block -> ring slot j % stages
+    const int r0 = (blockIdx.x + j * gridDim.x) * LN_SLAB;
+    const uint32_t bytes = static_cast<uint32_t>(min(rows - r0, LN_SLAB)) * d * 4;
+    const int slot = j % stages;
+    float* dst = ring + static_cast<size_t>(slot) * 3 * slab_floats;
+    mbar_arrive_expect_tx(bar0 + 8u * slot, (dres ? 3 : 2) * bytes);
+    bulk_load_1d(smem_u32(dst), x + static_cast<size_t>(r0) * d, bytes, bar0 + 8u * slot);
+    bulk_load_1d(smem_u32(dst + slab_floats), dy + static_cast<size_t>(r0) * d, bytes, bar0 + 8u * slot);
+    if (dres) bulk_load_1d(smem_u32(dst + 2 * slab_floats), dres + static_cast<size_t>(r0) * d, bytes, bar0 + 8u * slot);
+  };
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    for (int s = 0; s < stages; ++s) mbar_init(bar0 + 8u * s, 1);
     fence_barrier_init();
-    const uint32_t bytes = static_cast<uint32_t>(nr) * d * 4;
-    mbar_arrive_expect_tx(bar, 2 * bytes);
-    bulk_load_1d(smem_u32(xs), x + static_cast<size_t>(r0) * d, bytes, bar);
-    bulk_load_1d(smem_u32(ys), dy + static_cast<size_t>(r0) * d, bytes, bar);
+    for (int j = 0; j < stages - 1 && j < my_slabs; ++j) issue(j);
   }
   __syncthreads();
-  mbar_wait(bar, 0);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  // ---- phase 1
-  for (int rl = warp; rl < nr; rl += 8) {
-    const float4* xr = reinterpret_cast<const float4*>(xs + rl * d);
-    const float4* yr = reinterpret_cast<const float4*>(ys + rl * d);
-    float4 v[8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = lane + i * 32;
-      v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / d;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (lane + i * 32 < nv) {
-        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / d + 1e-5f);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = lane + i * 32;
-      if (idx < nv) {
-        const float4 gg = __ldg(g4 + idx);
-        const float4 u = yr[idx];
-        const float a0 = gg.x * u.x, a1 = gg.y * u.y, a2 = gg.z * u.z, a3 = gg.w * u.w;
-        s1 += (a0 + a1) + (a2 + a3);
-        s2 += (a0 * v[i].x + a1 * v[i].y) + (a2 * v[i].z + a3 * v[i].w);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) sstats[rl] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
-  }
-  __syncthreads();
-  // ---- phase 2
-  const int cg = threadIdx.x;  // column group (d <= 1024 -> nv <= 256)
-  if (cg >= nv) return;
-  const float4 gg = __ldg(g4 + cg);
+  const int cg = threadIdx.x;  // column group of phase 2 (d <= 1024 -> nv <= 256)
+  const float4 gg = cg < nv ? __ldg(g4 + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
-#pragma unroll 4
-  for (int rl = 0; rl < nr; ++rl) {
-    const size_t off = static_cast<size_t>(r0 + rl) * nv + cg;
-    const float4 xv = reinterpret_cast<const float4*>(xs + rl * d)[cg];
-    const float4 dyv = reinterpret_cast<const float4*>(ys + rl * d)[cg];
-    const float4 st = sstats[rl];  // mean, rstd, m1, m2
-    float4 xh;
-    xh.x = (xv.x - st.x) * st.y; xh.y = (xv.y - st.x) * st.y; xh.z = (xv.z - st.x) * st.y; xh.w = (xv.w - st.x) * st.y;
-    float4 o;
-    o.x = st.y * (gg.x * dyv.x - st.z - xh.x * st.w);
-    o.y = st.y * (gg.y * dyv.y - st.z - xh.y * st.w);
-    o.z = st.y * (gg.z * dyv.z - st.z - xh.z * st.w);
-    o.w = st.y * (gg.w * dyv.w - st.z - xh.w * st.w);
-    if (dres) {
-      const float4 rr = reinterpret_cast<const float4*>(dres)[off];
-      o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+  for (int j = 0; j < my_slabs; ++j) {
+    // slot (j - 1) % stages was released by the __syncthreads that ended the previous iteration
+    if (threadIdx.x == 0 && j + stages - 1 < my_slabs) issue(j + stages - 1);
+    const int slot = j % stages;
+    const int r0 = (blockIdx.x + j * gridDim.x) * LN_SLAB;
+    const int nr = min(rows - r0, LN_SLAB);
+    const float* xs = ring + static_cast<size_t>(slot) * 3 * slab_floats;
+    const float* ys = xs + slab_floats;
+    const float* rs = ys + slab_floats;
+    mbar_wait(bar0 + 8u * slot, (j / stages) & 1);
+    // ---- phase 1: warp w owns row w of the slab
+    if (warp < nr) {
+      const float4* xr = reinterpret_cast<const float4*>(xs + warp * d);
+      const float4* yr = reinterpret_cast<const float4*>(ys + warp * d);
+      float4 v[8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = lane + i * 32;
+        v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / d;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (lane + i * 32 < nv) {
+          v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+          q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / d + 1e-5f);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nv) {
+          const float4 gl = __ldg(g4 + idx);
+          const float4 u = yr[idx];
+          const float a0 = gl.x * u.x, a1 = gl.y * u.y, a2 = gl.z * u.z, a3 = gl.w * u.w;
+          s1 += (a0 + a1) + (a2 + a3);
+          s2 += (a0 * v[i].x + a1 * v[i].y) + (a2 * v[i].z + a3 * v[i].w);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) sstats[warp] = make_float4(mean, rstd, s1 / d, s2 * rstd / d);
     }
-    reinterpret_cast<float4*>(dx)[off] = o;
-    if (dx_b) reinterpret_cast<uint2*>(dx_b)[off] = make_uint2(cvt_bf16x2(o.x, o.y), cvt_bf16x2(o.z, o.w));
-    ag.x += dyv.x * xh.x; ag.y += dyv.y * xh.y; ag.z += dyv.z * xh.z; ag.w += dyv.w * xh.w;
-    ab.x += dyv.x; ab.y += dyv.y; ab.z += dyv.z; ab.w += dyv.w;
-    ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+    __syncthreads();
+    // ---- phase 2
+    if (cg < nv) {
+#pragma unroll 4
+      for (int rl = 0; rl < nr; ++rl) {
+        const size_t off = static_cast<size_t>(r0 + rl) * nv + cg;
+        const float4 xv = reinterpret_cast<const float4*>(xs + rl * d)[cg];
+        const float4 dyv = reinterpret_cast<const float4*>(ys + rl * d)[cg];
+        const float4 st = sstats[rl];  // mean, rstd, m1, m2
+        float4 xh;
+        xh.x = (xv.x - st.x) * st.y; xh.y = (xv.y - st.x) * st.y; xh.z = (xv.z - st.x) * st.y; xh.w = (xv.w - st.x) * st.y;
+        float4 o;
+        o.x = st.y * (gg.x * dyv.x - st.z - xh.x * st.w);
+        o.y = st.y * (gg.y * dyv.y - st.z - xh.y * st.w);
+        o.z = st.y * (gg.z * dyv.z - st.z - xh.z * st.w);
+        o.w = st.y * (gg.w * dyv.w - st.z - xh.w * st.w);
+        if (dres) {
+          const float4 rr = reinterpret_cast<const float4*>(rs + rl * d)[cg];
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        reinterpret_cast<float4*>(dx)[off] = o;
+        if (dx_b) reinterpret_cast<uint2*>(dx_b)[off] = make_uint2(cvt_bf16x2(o.x, o.y), cvt_bf16x2(o.z, o.w));
+        ag.x += dyv.x * xh.x; ag.y += dyv.y * xh.y; ag.z += dyv.z * xh.z; ag.w += dyv.w * xh.w;
+        ab.x += dyv.x; ab.y += dyv.y; ab.z += dyv.z; ab.w += dyv.w;
+        ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+      }
+    }
+    __syncthreads();  // the slot and sstats may be overwritten
   }
+  if (cg >= nv || my_slabs == 0) return;
   atomicAdd(dgamma + cg * 4 + 0, ag.x); atomicAdd(dgamma + cg * 4 + 1, ag.y);
   atomicAdd(dgamma + cg * 4 + 2, ag.z); atomicAdd(dgamma + cg * 4 + 3, ag.w);
   atomicAdd(dbeta + cg * 4 + 0, ab.x); atomicAdd(dbeta + cg * 4 + 1, ab.y);
@@ -756,14 +777,22 @@ int ln_backward(const float* x, const float* gamma, const float* dy, const float
   FACT_REQUIRE(dy != dx, FACT_ERR_BAD_SHAPE, "ln_backward: dx must not alias dy (it may alias dres)");
   FACT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, FACT_ERR_BAD_ALIGN,
                "ln_backward: x and dy must be 16-byte aligned");
-  const int smem = 2 * LN_ROWS_PER_BLOCK * d * 4 + LN_ROWS_PER_BLOCK * 16 + 16;
+  FACT_REQUIRE(!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0, FACT_ERR_BAD_ALIGN,
+               "ln_backward: dres must be 16-byte aligned");
+  const int slab_bytes = 3 * LN_SLAB * d * 4;
+  int stages = (220 * 1024) / slab_bytes;
+  stages = stages > 3 ? 3 : stages;
+  FACT_REQUIRE(stages >= 2, FACT_ERR_UNSUPPORTED, "ln_backward: d %d too wide for the shared-memory ring", d);
+  const int smem = stages * slab_bytes + LN_SLAB * 16 + stages * 8 + 16;
   static int smem_set = 0;
   if (smem > smem_set) {
     FACT_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  ln_bwd_kernel<<<(rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK, 256, smem, st>>>(
-      x, gamma, dy, dres, dx, static_cast<bf16*>(dx_b), dgamma, dbeta, colsum, rows, d);
+  const int num_slabs = (rows + LN_SLAB - 1) / LN_SLAB;
+  const int grid = num_slabs < num_sms() ? num_slabs : num_sms();
+  ln_bwd_kernel<<<grid, 256, smem, st>>>(x, gamma, dy, dres, dx, static_cast<bf16*>(dx_b), dgamma, dbeta, colsum, rows,
+                                         d, stages);
   FACT_LAUNCH_CHECK("ln_bwd_kernel");
   return FACT_OK;
 }
@@ -800,6 +829,33 @@ int slice_rows(const float* src, float* dst, long long rows_dst, int d, int seq_
   int grid = static_cast<int>((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
   slice_rows_kernel<<<grid, 256, 0, st>>>(src, dst, rows_dst, d, seq_dst, seq_src, seq_off);
   FACT_LAUNCH_CHECK("slice_rows_kernel");
+  return FACT_OK;
+}
+
+// dpos[t, c] += sum over clips of dy[clip * n_tok + t, c]  (PositionEmbedding gradient, base_models.py:148-156)
+__global__ void __launch_bounds__(256) pos_grad_kernel(const float* __restrict__ dy, float* __restrict__ dpos, int batch,
+                                                       int n_tok, int d) {
+  const int nv = d >> 2;
+  const int idx = blockIdx.x * 256 + threadIdx.x;  // (t, column group)
+  if (idx >= n_tok * nv) return;
+  const int t = idx / nv, cg = idx % nv;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+  for (int b = 0; b < batch; ++b) {
+    const float4 v = reinterpret_cast<const float4*>(dy + (static_cast<size_t>(b) * n_tok + t) * d)[cg];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  float4* o = reinterpret_cast<float4*>(dpos + static_cast<size_t>(t) * d) + cg;
+  float4 cur = *o;
+  cur.x += s.x; cur.y += s.y; cur.z += s.z; cur.w += s.w;
+  *o = cur;
+}
+
+int pos_grad(const float* dy, float* dpos, int batch, int n_tok, int d, cudaStream_t st) {
+  FACT_REQUIRE(d % 4 == 0, FACT_ERR_BAD_SHAPE, "pos_grad: d %d", d);
+  const int total = n_tok * (d / 4);
+  pos_grad_kernel<<<(total + 255) / 256, 256, 0, st>>>(dy, dpos, batch, n_tok, d);
+  FACT_LAUNCH_CHECK("pos_grad_kernel");
   return FACT_OK;
 }
 

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------- weight packing
 // w [k_in, n_out] fp32 row-major  ->  hi/lo [n_out, k_in] bf16 (transpose through a padded shared tile)
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ hi,
-                                                          bf16* __restrict__ lo, int k_in, int n_out) {
+                                                          bf16* __restrict__ lo, int k_in, int n_out, int ld) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     if (n < n_out && k < k_in) {
       bf16 h, l;
       split_bf16(tile[tx][r], h, l);
-      hi[static_cast<size_t>(n) * k_in + k] = h;
-      if (lo) lo[static_cast<size_t>(n) * k_in + k] = l;
+      hi[static_cast<size_t>(n) * ld + k] = h;
+      if (lo) lo[static_cast<size_t>(n) * ld + k] = l;
     }
   }
 }
@@ -303,6 +303,7 @@ static int check_epi(const fact_gemm_epilogue* e) {
   FACT_REQUIRE(split_out ? e->out_hi != nullptr : e->out_f32 != nullptr, FACT_ERR_BAD_SHAPE,
                "epilogue output buffer missing");
   FACT_REQUIRE(e->kind != FACT_EPI_BIAS_RESID_F32 || e->resid, FACT_ERR_BAD_SHAPE, "resid epilogue needs resid");
+  FACT_REQUIRE(e->resid_rows == 0, FACT_ERR_UNSUPPORTED, "resid_rows is a tensor-path (fact_gemm) option");
   return FACT_OK;
 }
 
@@ -450,11 +451,49 @@ extern "C" int fact_layernorm_split(const float* x, const float* gamma, const fl
   return FACT_OK;
 }
 
+namespace fact {
+// ---- tensor-core embedding (large batches): LinearEmbedding as a tcgen05 GEMM on split inputs
+// x rows -> bf16 hi / lo with row pitch kp (>= f, multiple of 8; the pad is never read: the TMA map is f wide).
+// Row r = clip r / n_tok, frame start + r % n_tok (the AR window: start = *step_ptr), as in the CUDA-core path.
+__global__ void __launch_bounds__(256) embed_prep_kernel(const float* __restrict__ x, long long batch_stride,
+                                                         const int* __restrict__ step_ptr, bf16* __restrict__ hi,
+                                                         bf16* __restrict__ lo, int rows, int n_tok, int f, int kp) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int start = step_ptr ? *step_ptr : 0;
+  const float* src = x + static_cast<size_t>(row / n_tok) * batch_stride + static_cast<size_t>(start + row % n_tok) * f;
+  for (int c = lane; c < f; c += 32) {
+    bf16 h, l;
+    split_bf16(src[c], h, l);
+    hi[static_cast<size_t>(row) * kp + c] = h;
+    if (lo) lo[static_cast<size_t>(row) * kp + c] = l;
+  }
+}
+
+int embed_prep(const float* x, long long batch_stride, const int* step_ptr, void* hi, void* lo, int rows, int n_tok,
+               int f, int kp, cudaStream_t st) {
+  embed_prep_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, batch_stride, step_ptr, static_cast<bf16*>(hi),
+                                                    static_cast<bf16*>(lo), rows, n_tok, f, kp);
+  FACT_LAUNCH_CHECK("embed_prep_kernel launch");
+  return FACT_OK;
+}
+
+// w [k_in, n_out] fp32 -> hi / lo [n_out, ld] bf16 (ld >= k_in)
+int pack_weight_ld(const float* w, void* hi, void* lo, int k_in, int n_out, int ld, cudaStream_t st) {
+  dim3 grid((n_out + 31) / 32, (k_in + 31) / 32);
+  pack_weight_kernel<<<grid, 256, 0, st>>>(w, static_cast<bf16*>(hi), static_cast<bf16*>(lo), k_in, n_out, ld);
+  FACT_LAUNCH_CHECK("pack_weight_kernel launch");
+  return FACT_OK;
+}
+
+}  // namespace fact
+using namespace fact;
+
 extern "C" int fact_pack_weight(const float* w_keras, void* hi, void* lo, int k_in, int n_out, void* stream) {
   FACT_REQUIRE(w_keras && hi && k_in > 0 && n_out > 0, FACT_ERR_BAD_SHAPE, "fact_pack_weight: bad arguments");
   dim3 grid((n_out + 31) / 32, (k_in + 31) / 32);
   pack_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_keras, static_cast<bf16*>(hi), static_cast<bf16*>(lo),
-                                                          k_in, n_out);
+                                                          k_in, n_out, k_in);
   FACT_LAUNCH_CHECK("pack_weight_kernel launch");
   return FACT_OK;
 }

@@ -33,7 +33,12 @@ struct Workspace {
   bf16 *a_ln_hi, *a_ln_lo, *a_ao_hi, *a_ao_lo, *a_qkv_hi, *a_qkv_lo, *a_h_hi, *a_h_lo;
   float* a_splitk;
   size_t a_splitk_bytes;
+  // tensor-core embedding (batch * seq >= kEmbedTcMinRows): split inputs and packed LinearEmbedding kernels
+  bf16 *em_x_hi, *em_x_lo, *ea_x_hi, *ea_x_lo;   // [tokens, kp]
+  bf16 *em_w_hi, *em_w_lo, *ea_w_hi, *ea_w_lo;   // [d, kp]
+  int em_kp, ea_kp;
 };
+constexpr size_t kEmbedTcMinRows = 2048;  // below this the single CUDA-core launch wins (batch-1 decode)
 
 int g_dual_stream = 1;  // fact_set_flag("dual_stream", 0): run both modality encoders on the caller's stream
 constexpr size_t kDualStreamMaxTokens = 4096;  // audio tokens (batch * 240) up to which the encoders run concurrently
@@ -78,6 +83,18 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
     w.a_h_lo = lo ? reinterpret_cast<bf16*>(take(ta * ff * 2)) : nullptr;
     w.a_splitk_bytes = 16 * (ta < 1024 ? ta : 1024) * (3 * d > ff ? 3 * d : ff) * 4;
     w.a_splitk = reinterpret_cast<float*>(take(w.a_splitk_bytes));
+  }
+  if (mode != FACT_MODE_FP32_SIMT && tm >= kEmbedTcMinRows) {
+    w.em_kp = (dm->motion_dim + 7) / 8 * 8;
+    w.ea_kp = (dm->audio_dim + 7) / 8 * 8;
+    w.em_x_hi = reinterpret_cast<bf16*>(take(tm * w.em_kp * 2));
+    w.em_x_lo = lo ? reinterpret_cast<bf16*>(take(tm * w.em_kp * 2)) : nullptr;
+    w.ea_x_hi = reinterpret_cast<bf16*>(take(ta * w.ea_kp * 2));
+    w.ea_x_lo = lo ? reinterpret_cast<bf16*>(take(ta * w.ea_kp * 2)) : nullptr;
+    w.em_w_hi = reinterpret_cast<bf16*>(take(d * w.em_kp * 2));
+    w.em_w_lo = lo ? reinterpret_cast<bf16*>(take(d * w.em_kp * 2)) : nullptr;
+    w.ea_w_hi = reinterpret_cast<bf16*>(take(d * w.ea_kp * 2));
+    w.ea_w_lo = lo ? reinterpret_cast<bf16*>(take(d * w.ea_kp * 2)) : nullptr;
   }
   if (ws) *ws = w;
   return off;
@@ -224,6 +241,42 @@ static int run_stack(const fact_dims* dm, const fact_layer_weights* layers, int 
   return FACT_OK;
 }
 
+int embed_prep(const float* x, long long batch_stride, const int* step_ptr, void* hi, void* lo, int rows, int n_tok,
+               int f, int kp, cudaStream_t st);                                                       // elementwise.cu
+int pack_weight_ld(const float* w, void* hi, void* lo, int k_in, int n_out, int ld, cudaStream_t st);  // elementwise.cu
+
+// Once per fact_forward / fact_infer_auto_regressive call (outside the captured frame): K-major split copies of the two
+// LinearEmbedding kernels for the tensor-core embedding.
+static int pack_embed_weights(const fact_dims* dm, const fact_weights* w, const Workspace& ws, cudaStream_t st) {
+  if (!ws.em_x_hi) return FACT_OK;
+  int rc;
+  if ((rc = pack_weight_ld(w->motion_embed_w, ws.em_w_hi, ws.em_w_lo, dm->motion_dim, dm->d_model, ws.em_kp, st)))
+    return rc;
+  return pack_weight_ld(w->audio_embed_w, ws.ea_w_hi, ws.ea_w_lo, dm->audio_dim, dm->d_model, ws.ea_kp, st);
+}
+
+// LinearEmbedding + bias + PositionEmbedding (base_models.py:130-156).  Large batches: inputs split to bf16 hi / lo
+// and the product runs on the tensor path (the position table enters as a broadcast residual); otherwise one
+// CUDA-core fp32 launch.
+static int embed(const float* x, long long bs, const int* step_ptr, const float* w_f32, const float* bias,
+                 const float* pos, float* y, int batch, int n_tok, int f, int d, int mode, bf16* x_hi, bf16* x_lo,
+                 const bf16* w_hi, const bf16* w_lo, int kp, cudaStream_t st) {
+  if (!x_hi) return fact_embed(x, bs, step_ptr, w_f32, bias, pos, y, batch, n_tok, f, d, st);
+  const int rows = batch * n_tok;
+  int rc;
+  if ((rc = embed_prep(x, bs, step_ptr, x_hi, x_lo, rows, n_tok, f, kp, st))) return rc;
+  fact_gemm_epilogue e{};
+  e.kind = FACT_EPI_BIAS_RESID_F32;
+  e.out_f32 = y;
+  e.ldo = d;
+  e.bias = bias;
+  e.resid = pos;
+  e.ldr = d;
+  e.resid_rows = n_tok;
+  return fact_gemm(x_hi, mode == FACT_MODE_PRECISE ? x_lo : nullptr, kp, w_hi, mode == FACT_MODE_PRECISE ? w_lo : nullptr,
+                   kp, rows, d, f, &e, st);
+}
+
 // embeddings + modality encoders + 12-layer cross-modal stack; leaves the result in ws.xc
 static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* motion, long long motion_bs,
                      const float* audio, long long audio_bs, const int* step_ptr, int batch, int mode,
@@ -252,16 +305,16 @@ static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* mo
     wa.splitk = ws.a_splitk; wa.splitk_bytes = ws.a_splitk_bytes;
     FACT_CUDA_CHECK(cudaEventRecord(ev_fork, st));
     FACT_CUDA_CHECK(cudaStreamWaitEvent(sa, ev_fork, 0));
-    if ((rc = fact_embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
-                         dm->audio_seq, dm->audio_dim, d, sa)))
+    if ((rc = embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
+                    dm->audio_seq, dm->audio_dim, d, mode, ws.ea_x_hi, ws.ea_x_lo, ws.ea_w_hi, ws.ea_w_lo, ws.ea_kp, sa)))
       return rc;
     if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, wa, ws.xc, ns,
                         dm->motion_seq, sa)))
       return rc;
     FACT_CUDA_CHECK(cudaEventRecord(ev_join, sa));
   }
-  if ((rc = fact_embed(motion, motion_bs, step_ptr, w->motion_embed_w, w->motion_embed_b, w->motion_pos, ws.xm, batch,
-                       dm->motion_seq, dm->motion_dim, d, st)))
+  if ((rc = embed(motion, motion_bs, step_ptr, w->motion_embed_w, w->motion_embed_b, w->motion_pos, ws.xm, batch,
+                  dm->motion_seq, dm->motion_dim, d, mode, ws.em_x_hi, ws.em_x_lo, ws.em_w_hi, ws.em_w_lo, ws.em_kp, st)))
     return rc;
   if ((rc = run_stack(dm, w->motion_layers, dm->motion_layers, ws.xm, batch, dm->motion_seq, mode, ws, ws.xc, ns, 0,
                       st)))
@@ -269,8 +322,8 @@ static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* mo
   if (dual) {
     FACT_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));   // join before the cross-modal stack reads xc
   } else {
-    if ((rc = fact_embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
-                         dm->audio_seq, dm->audio_dim, d, st)))
+    if ((rc = embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
+                    dm->audio_seq, dm->audio_dim, d, mode, ws.ea_x_hi, ws.ea_x_lo, ws.ea_w_hi, ws.ea_w_lo, ws.ea_kp, st)))
       return rc;
     if ((rc = run_stack(dm, w->audio_layers, dm->audio_layers, ws.xa, batch, dm->audio_seq, mode, ws, ws.xc, ns,
                         dm->motion_seq, st)))
@@ -332,6 +385,7 @@ extern "C" int fact_forward(const fact_dims* dims, const fact_weights* w, const 
   cudaStream_t st = as_stream(stream);
   const long long mbs = static_cast<long long>(dims->motion_seq) * dims->motion_dim;
   const long long abs_ = static_cast<long long>(dims->audio_seq) * dims->audio_dim;
+  if ((rc = pack_embed_weights(dims, w, ws, st))) return rc;
   if ((rc = run_trunk(dims, w, motion, mbs, audio, abs_, nullptr, batch, mode, ws, false, st))) return rc;
   // output Dense on all 360 rows (base_models.py:200)
   const int d = dims->d_model, ns = dims->motion_seq + dims->audio_seq, M = batch * ns;
@@ -376,6 +430,10 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
   const long long audio_bs = static_cast<long long>(audio_len) * dims->audio_dim;
   FACT_REQUIRE(dims->out_dim == dims->motion_dim, FACT_ERR_BAD_SHAPE,
                "AR feedback needs out_dim == motion feature dim (fact_model.py:131)");
+  {  // outside the per-frame graph: the embedding kernels may have changed since the last call
+    const int rc = pack_embed_weights(dims, w, ws, st);
+    if (rc) return rc;
+  }
 
   auto one_frame = [&](cudaStream_t s) -> int {
     int r;

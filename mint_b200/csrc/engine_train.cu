@@ -26,6 +26,10 @@ int slice_rows(const float* src, float* dst, long long rows_dst, int d, int seq_
                cudaStream_t st);
 int embed_backward(const float* x, long long x_batch_stride, const float* dy, float* dW, float* dbias, float* dpos,
                    int batch, int n_tok, int f, int d, cudaStream_t st);
+int pos_grad(const float* dy, float* dpos, int batch, int n_tok, int d, cudaStream_t st);
+int embed_prep(const float* x, long long batch_stride, const int* step_ptr, void* hi, void* lo, int rows, int n_tok,
+               int f, int kp, cudaStream_t st);
+int pack_weight_ld(const float* w, void* hi, void* lo, int k_in, int n_out, int ld, cudaStream_t st);
 
 struct SavedLayer {
   float* x_in;   // [M, d]   input of the layer (residual stream)
@@ -50,6 +54,9 @@ struct TrainWs {
   float *dy, *dym, *dya, *dln;  // [Mc, d] fp32 (dym / dya: encoder-sized)
   bf16 *dy_b, *dz_b, *dao_b, *dqkv_b;
   float *Dscr, *dq_scr, *ln_stats;
+  // LinearEmbedding on the tensor path: bf16 inputs [tokens, kp] (kept for the weight gradient), kernels [d, kp]
+  bf16 *em_x, *ea_x, *em_w, *ea_w;
+  int em_kp, ea_kp;
 };
 
 static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
@@ -104,6 +111,12 @@ static size_t carve_train(const fact_dims* dm, int batch, void* base, TrainWs* w
   w.Dscr = reinterpret_cast<float*>(take(static_cast<size_t>(batch) * H * seq[2] * 4));
   w.dq_scr = reinterpret_cast<float*>(take(Mc * d * 4));
   w.ln_stats = reinterpret_cast<float*>(take(Mc * 16));
+  w.em_kp = (dm->motion_dim + 7) / 8 * 8;
+  w.ea_kp = (dm->audio_dim + 7) / 8 * 8;
+  w.em_x = reinterpret_cast<bf16*>(take(Mm * w.em_kp * 2));
+  w.ea_x = reinterpret_cast<bf16*>(take(Ma * w.ea_kp * 2));
+  w.em_w = reinterpret_cast<bf16*>(take(d * w.em_kp * 2));
+  w.ea_w = reinterpret_cast<bf16*>(take(d * w.ea_kp * 2));
   if (ws) *ws = w;
   return off;
 }
@@ -111,6 +124,33 @@ static size_t carve_train(const fact_dims* dm, int batch, void* base, TrainWs* w
 static int bf16_gemm(const bf16* a, int lda, const void* w, int ldw, int m, int n, int k, const fact_gemm_epilogue* e,
                      cudaStream_t st) {
   return fact_gemm(a, nullptr, lda, w, nullptr, ldw, m, n, k, e, st);
+}
+
+// LinearEmbedding + bias + PositionEmbedding (base_models.py:130-156) as a tensor-core GEMM on the bf16 inputs; the
+// position table enters as a residual broadcast over the clips.  x_b is kept for the weight gradient.
+static int embed_fwd_train(const float* x, const float* w_f32, const float* bias, const float* pos, float* y,
+                           bf16* x_b, bf16* w_b, int kp, int batch, int n_tok, int f, int d, cudaStream_t st) {
+  const int rows = batch * n_tok;
+  int rc;
+  if ((rc = embed_prep(x, static_cast<long long>(n_tok) * f, nullptr, x_b, nullptr, rows, n_tok, f, kp, st))) return rc;
+  if ((rc = pack_weight_ld(w_f32, w_b, nullptr, f, d, kp, st))) return rc;
+  fact_gemm_epilogue e{};
+  e.kind = FACT_EPI_BIAS_RESID_F32;
+  e.out_f32 = y;
+  e.ldo = d;
+  e.bias = bias;
+  e.resid = pos;
+  e.ldr = d;
+  e.resid_rows = n_tok;
+  return bf16_gemm(x_b, kp, w_b, kp, rows, d, f, &e, st);
+}
+
+// dy_b / the bias gradient were already produced by the LayerNorm backward of the encoder's first layer
+static int embed_bwd_train(const bf16* x_b, int kp, const float* dy, const bf16* dy_b, float* dW, float* dpos, int batch,
+                           int n_tok, int f, int d, cudaStream_t st) {
+  int rc;
+  if ((rc = wgrad_gemm(x_b, kp, dy_b, d, dW, d, batch * n_tok, f, d, st))) return rc;
+  return pos_grad(dy, dpos, batch, n_tok, d, st);
 }
 
 // forward of one layer, saving what the backward needs; `out` = where the layer's output residual stream goes
@@ -246,8 +286,8 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   int rc;
 
   // ------------------------------------------------------------------ forward (saves activations)
-  if ((rc = fact_embed(motion, static_cast<long long>(dims->motion_seq) * dims->motion_dim, nullptr, w->motion_embed_w,
-                       w->motion_embed_b, w->motion_pos, Sm[0].x_in, batch, dims->motion_seq, dims->motion_dim, d, st)))
+  if ((rc = embed_fwd_train(motion, w->motion_embed_w, w->motion_embed_b, w->motion_pos, Sm[0].x_in, ws.em_x, ws.em_w,
+                            ws.em_kp, batch, dims->motion_seq, dims->motion_dim, d, st)))
     return rc;
   for (int l = 0; l < dims->motion_layers; ++l) {
     const bool last = l + 1 == dims->motion_layers;
@@ -255,8 +295,8 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
                               last ? Sc[0].x_in : Sm[l + 1].x_in, last ? ns : 0, 0, st)))
       return rc;
   }
-  if ((rc = fact_embed(audio, static_cast<long long>(dims->audio_seq) * dims->audio_dim, nullptr, w->audio_embed_w,
-                       w->audio_embed_b, w->audio_pos, Sa[0].x_in, batch, dims->audio_seq, dims->audio_dim, d, st)))
+  if ((rc = embed_fwd_train(audio, w->audio_embed_w, w->audio_embed_b, w->audio_pos, Sa[0].x_in, ws.ea_x, ws.ea_w,
+                            ws.ea_kp, batch, dims->audio_seq, dims->audio_dim, d, st)))
     return rc;
   for (int l = 0; l < dims->audio_layers; ++l) {
     const bool last = l + 1 == dims->audio_layers;
@@ -299,18 +339,18 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   if ((rc = slice_rows(ws.dy, ws.dya, static_cast<long long>(batch) * dims->audio_seq, d, dims->audio_seq, ns,
                        dims->motion_seq, st)))
     return rc;
+  // each encoder's first-layer LayerNorm backward also emits bf16(dy) and its column sums = the embedding bias gradient
   for (int l = dims->motion_layers - 1; l >= 0; --l)
     if ((rc = layer_bwd(dims, w->motion_layers[l], g->motion_layers[l], Sm[l], batch, dims->motion_seq, ws.dym, ws,
-                        l + 1 < dims->motion_layers, l > 0 ? g->motion_layers[l - 1].b2 : nullptr, st)))
+                        l + 1 < dims->motion_layers, l > 0 ? g->motion_layers[l - 1].b2 : g->motion_embed_b, st)))
       return rc;
+  if ((rc = embed_bwd_train(ws.em_x, ws.em_kp, ws.dym, ws.dy_b, g->motion_embed_w, g->motion_pos, batch,
+                            dims->motion_seq, dims->motion_dim, d, st)))
+    return rc;
   for (int l = dims->audio_layers - 1; l >= 0; --l)
     if ((rc = layer_bwd(dims, w->audio_layers[l], g->audio_layers[l], Sa[l], batch, dims->audio_seq, ws.dya, ws,
-                        l + 1 < dims->audio_layers, l > 0 ? g->audio_layers[l - 1].b2 : nullptr, st)))
+                        l + 1 < dims->audio_layers, l > 0 ? g->audio_layers[l - 1].b2 : g->audio_embed_b, st)))
       return rc;
-  if ((rc = embed_backward(motion, static_cast<long long>(dims->motion_seq) * dims->motion_dim, ws.dym,
-                           g->motion_embed_w, g->motion_embed_b, g->motion_pos, batch, dims->motion_seq,
-                           dims->motion_dim, d, st)))
-    return rc;
-  return embed_backward(audio, static_cast<long long>(dims->audio_seq) * dims->audio_dim, ws.dya, g->audio_embed_w,
-                        g->audio_embed_b, g->audio_pos, batch, dims->audio_seq, dims->audio_dim, d, st);
+  return embed_bwd_train(ws.ea_x, ws.ea_kp, ws.dya, ws.dy_b, g->audio_embed_w, g->audio_pos, batch, dims->audio_seq,
+                         dims->audio_dim, d, st);
 }

@@ -44,6 +44,7 @@ struct EpiArgs {
   int ldaux;
   int reduce_add;  // TMA-store epilogue, BIAS_RESID_F32 with out == resid: the add is a bulk reduction in the L2
   float* colsum;   // TMA-store epilogue, GELU_GRAD: += column sums of the staged bf16 box (bias gradient)
+  int resid_rows;  // > 0: resid is a [resid_rows, ldr] table read at row % resid_rows (the position embedding)
 };
 
 template <int BN, int NPART, int STAGES>
@@ -61,6 +62,9 @@ struct GemmCfg {
   static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier block too small");
 };
 
+__device__ __forceinline__ size_t resid_row(int row, const EpiArgs& e) {
+  return static_cast<size_t>(e.resid_rows > 0 ? row % e.resid_rows : row);
+}
 __device__ __forceinline__ int map_row(int row, const EpiArgs& e) {
   if (e.seq_in == 0) return row;
   return (row / e.seq_in) * e.seq_out + e.seq_off + (row % e.seq_in);
@@ -92,7 +96,7 @@ __device__ __forceinline__ void epilogue_chunk(const float* v, const float4* rv,
         reinterpret_cast<float4*>(orow)[i] = o;
       }
     } else {
-      const float* rrow = ep.resid + static_cast<size_t>(row) * ep.ldr + col0;
+      const float* rrow = ep.resid + resid_row(row, ep) * ep.ldr + col0;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         if (col0 + c < N) {
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
       float4 rv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* rrow = (EPI == FACT_EPI_BIAS_RESID_F32 && row_ok) ? ep.resid + static_cast<size_t>(row) * ep.ldr
+      const float* rrow = (EPI == FACT_EPI_BIAS_RESID_F32 && row_ok) ? ep.resid + resid_row(row, ep) * ep.ldr
                                                                       : nullptr;
       if (EPI == FACT_EPI_BIAS_RESID_F32 && ep.vec_ok && row_ok && n0 + half * 32 + 32 <= N) {
 #pragma unroll
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
         if (nt < num_tiles) {
           const int nrow = (nt / tiles_n) * BM + 0 + q * 32 + lane;
           if (nrow < M) {
-            const float* nr = ep.resid + static_cast<size_t>(nrow) * ep.ldr + (nt % tiles_n) * BN;
+            const float* nr = ep.resid + resid_row(nrow, ep) * ep.ldr + (nt % tiles_n) * BN;
 #pragma unroll
             for (int c = half; c < BN / 32; c += 2) prefetch_l2(nr + c * 32);
           }
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(256) gemm_finish_kernel(const float* __restric
       x += ep.bias[col];
     }
     if (kind == FACT_EPI_BIAS_GELU_SPLIT) x = gelu_tanh(x);
-    if (kind == FACT_EPI_BIAS_RESID_F32) x += ep.resid[static_cast<size_t>(row) * ep.ldr + col];
+    if (kind == FACT_EPI_BIAS_RESID_F32) x += ep.resid[resid_row(row, ep) * ep.ldr + col];
     if (kind == FACT_EPI_SPLIT || kind == FACT_EPI_BIAS_GELU_SPLIT) {
       bf16 h, l;
       split_bf16(x, h, l);
@@ -578,7 +582,7 @@ __device__ __forceinline__ void epilogue_compute(const float* v, int row, int co
 #pragma unroll
     for (int c = 0; c < 32; ++c) of[c] = v[c] + b[c];
     if (EPI == FACT_EPI_BIAS_RESID_F32 && !ep.reduce_add && row_ok) {
-      const float* rrow = ep.resid + static_cast<size_t>(row) * ep.ldr + col0;
+      const float* rrow = ep.resid + resid_row(row, ep) * ep.ldr + col0;
       if (ep.vec_ok && col0 + 32 <= N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -846,7 +850,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       float4 rv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* rrow = (EPI == FACT_EPI_BIAS_RESID_F32 && row_ok) ? ep.resid + static_cast<size_t>(row) * ep.ldr
+      const float* rrow = (EPI == FACT_EPI_BIAS_RESID_F32 && row_ok) ? ep.resid + resid_row(row, ep) * ep.ldr
                                                                       : nullptr;
       if (EPI == FACT_EPI_BIAS_RESID_F32 && ep.vec_ok && row_ok && n0 + half * 32 + 32 <= N) {
 #pragma unroll
@@ -859,7 +863,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         if (nt < num_tiles) {
           const int nrow = (nt / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + q * 32 + lane;
           if (nrow < M) {
-            const float* nr = ep.resid + static_cast<size_t>(nrow) * ep.ldr + (nt % tiles_n) * BN;
+            const float* nr = ep.resid + resid_row(nrow, ep) * ep.ldr + (nt % tiles_n) * BN;
 #pragma unroll
             for (int c = half; c < BN / 32; c += 2) prefetch_l2(nr + c * 32);
           }
@@ -1199,6 +1203,7 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
   ep.ldaux = epi->ldaux;
   ep.reduce_add = 0;
   ep.colsum = nullptr;
+  ep.resid_rows = epi->resid_rows;
   if (split_out)
     ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
                 (!ep.bias || aligned16(ep.bias)) && (!ep.aux || (aligned16(ep.aux) && ep.ldaux % 8 == 0));

@@ -247,6 +247,44 @@ def test_gemm_tc_remap(fact_lib, cuda):
     _gemm_case(fact_lib, cuda, 3 * 240, 800, 3072, L.EPI_BIAS_RESID_F32, False, remap=(240, 360, 120))
 
 
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("m,seq,pair", [(2400, 120, 2), (2400, 120, 0), (480, 240, 0), (15360, 120, 1)])
+def test_gemm_embedding_shape_broadcast_residual(fact_lib, cuda, m, seq, pair, precise):
+    """The tensor-core LinearEmbedding: K = 225 inside a 232-element pitch (pad never read), position table as a
+    [seq, d] residual broadcast over the clips (resid_rows), through the pair, 1-SM and split-K kernels."""
+    n, k, ld = 800, 225, 232
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda)
+    bias = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    pos = torch.randn(seq, n, generator=g).to(cuda)
+
+    def padded(t):
+        hi, lo = split_ref(t)
+        out_hi = torch.full((t.shape[0], ld), float("nan"), dtype=torch.bfloat16, device=cuda)
+        out_lo = torch.full_like(out_hi, float("nan"))
+        out_hi[:, :k], out_lo[:, :k] = hi, lo
+        return out_hi, out_lo, (join(hi, lo) if precise else hi.float()).double()
+
+    a_hi, a_lo, a_eff = padded(a)
+    w_hi, w_lo, w_eff = padded(w)
+    out = torch.full((m, n), float("nan"), device=cuda)
+    scratch = torch.full((8 * m * n,), float("nan"), device=cuda) if m <= 1024 else None
+    e = _epi(kind=L.EPI_BIAS_RESID_F32, out_f32=out, ldo=n, bias=bias, resid=pos, ldr=n)
+    e.resid_rows = seq
+    if scratch is not None:
+        e.splitk_scratch, e.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
+    fact_lib.fact_set_flag(b"gemm_pair", pair)
+    try:
+        L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, ld, w_hi.data_ptr(),
+                                   w_lo.data_ptr() if precise else None, ld, m, n, k, C.byref(e), _st()))
+        torch.cuda.synchronize()
+    finally:
+        fact_lib.fact_set_flag(b"gemm_pair", 1)
+    ref = a_eff @ w_eff.t() + bias.double() + pos.double().repeat(m // seq, 1)
+    assert rel_err(out.double(), ref) < 3e-5
+
+
 def test_gemm_tc_inplace_residual(fact_lib, cuda):
     """out-proj / FF2 write the residual stream in place (out == resid)."""
     m, n, k = 360, 800, 800
