@@ -175,6 +175,14 @@ typedef struct fact_gemm_epilogue {
   /* FACT_EPI_BIAS_RESID_F32, optional: > 0 makes resid a [resid_rows, ldr] table read at row % resid_rows (the
    * position embedding added to every clip, base_models.py:148-156); 0 = resid has one row per output row. */
   int resid_rows;
+  /* FACT_EPI_BIAS_RESID_F32 without row remap, optional: after the output rows are final also write
+   * LayerNorm(out row; gamma, beta, eps 1e-5) split into bf16 hi / lo [m, n] (pitch n) -- the operand of the GEMM that
+   * follows in a pre-norm transformer (base_models.py:27-31).  Small m: fused into the split-K finish kernel; otherwise
+   * the LayerNorm launch follows the GEMM inside the call.  ln_hi NULL = off; ln_lo NULL = single bf16. */
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* ln_hi;
+  void* ln_lo;
 } fact_gemm_epilogue;
 
 /* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).

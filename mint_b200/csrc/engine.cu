@@ -131,14 +131,22 @@ static int dense(int mode, const bf16* a_hi, const bf16* a_lo, int lda, const vo
 }
 
 // One transformer layer on x [tokens, d] (in place unless `dst` remaps the final residual write).
+// ln1_done: ws.ln_hi / ln_lo already hold LayerNorm1(x) (the previous layer's FF2 call produced it); next: the layer
+// that follows in the same stack, whose LayerNorm1 the FF2 call of this layer produces (NULL: nobody, or remapped dst).
+// The LayerNorm rides on the GEMM call (fact_gemm_epilogue.ln_*): fused into the split-K finish kernel for small
+// batches, a separate launch inside the call otherwise -- the same kernels as before at large batch.
 static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x, int batch, int seq, int mode,
-                     const Workspace& ws, float* dst, int dst_seq, int dst_off, cudaStream_t st) {
+                     const Workspace& ws, float* dst, int dst_seq, int dst_off, bool ln1_done,
+                     const fact_layer_weights* next, cudaStream_t st) {
   const int d = dm->d_model, ff = dm->d_ff, H = dm->n_heads, dh = d / H;
   const int M = batch * seq;
   const bool lo = mode != FACT_MODE_BF16;
+  const bool ride = mode != FACT_MODE_FP32_SIMT;  // the CUDA-core debug GEMM has no LayerNorm option
   int rc;
   // --- Residual(Norm(Attention))
-  if ((rc = fact_layernorm_split(x, L.ln1_gamma, L.ln1_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
+  if (!ln1_done &&
+      (rc = fact_layernorm_split(x, L.ln1_gamma, L.ln1_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st)))
+    return rc;
   fact_gemm_epilogue e{};
   e.kind = FACT_EPI_SPLIT;
   e.out_hi = ws.qkv_hi;
@@ -156,9 +164,16 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
   e.bias = L.bo;
   e.resid = x;
   e.ldr = d;
+  if (ride) {  // --- Residual(Norm(MLP)): LayerNorm2 of the rows this call writes
+    e.ln_gamma = L.ln2_gamma;
+    e.ln_beta = L.ln2_beta;
+    e.ln_hi = ws.ln_hi;
+    e.ln_lo = lo ? ws.ln_lo : nullptr;
+  }
   if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, d, L.wo_hi, L.wo_lo, L.wo_f32, M, d, d, &e, st, &ws))) return rc;
-  // --- Residual(Norm(MLP))
-  if ((rc = fact_layernorm_split(x, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st))) return rc;
+  if (!ride &&
+      (rc = fact_layernorm_split(x, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, M, d, st)))
+    return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_BIAS_GELU_SPLIT;
   e.out_hi = ws.h_hi;
@@ -177,6 +192,11 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
     e.seq_in = seq;
     e.seq_out = dst_seq;
     e.seq_off = dst_off;
+  } else if (next && ride) {  // LayerNorm1 of the next layer of this stack
+    e.ln_gamma = next->ln1_gamma;
+    e.ln_beta = next->ln1_beta;
+    e.ln_hi = ws.ln_hi;
+    e.ln_lo = lo ? ws.ln_lo : nullptr;
   }
   return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, M, d, ff, &e, st, &ws);
 }
@@ -211,8 +231,16 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
   e.bias = L.bo;
   e.resid = x;
   e.ldr = pitch;
+  const bool ride = mode != FACT_MODE_FP32_SIMT;
+  if (ride) {
+    e.ln_gamma = L.ln2_gamma;
+    e.ln_beta = L.ln2_beta;
+    e.ln_hi = ws.ln_hi;
+    e.ln_lo = lo ? ws.ln_lo : nullptr;
+  }
   if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, pitch, L.wo_hi, L.wo_lo, L.wo_f32, batch, d, d, &e, st, &ws))) return rc;
-  if ((rc = fact_layernorm_split(ws.xr, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, batch, d, st)))
+  if (!ride &&
+      (rc = fact_layernorm_split(ws.xr, L.ln2_gamma, L.ln2_beta, ws.ln_hi, lo ? ws.ln_lo : nullptr, batch, d, st)))
     return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_BIAS_GELU_SPLIT;
@@ -233,9 +261,12 @@ static int run_layer_row0(const fact_dims* dm, const fact_layer_weights& L, floa
 
 static int run_stack(const fact_dims* dm, const fact_layer_weights* layers, int n_layers, float* x, int batch,
                      int seq, int mode, const Workspace& ws, float* dst, int dst_seq, int dst_off, cudaStream_t st) {
+  const bool ride = mode != FACT_MODE_FP32_SIMT;
   for (int i = 0; i < n_layers; ++i) {
     const bool last = i + 1 == n_layers;
-    int rc = run_layer(dm, layers[i], x, batch, seq, mode, ws, last ? dst : nullptr, dst_seq, dst_off, st);
+    // layer i's FF2 call leaves LayerNorm1 of layer i + 1 in ws.ln_hi / ln_lo
+    int rc = run_layer(dm, layers[i], x, batch, seq, mode, ws, last ? dst : nullptr, dst_seq, dst_off, ride && i > 0,
+                       last ? nullptr : &layers[i + 1], st);
     if (rc) return rc;
   }
   return FACT_OK;
@@ -347,7 +378,7 @@ static int check_weights(const fact_dims* dm, const fact_weights* w) {
 
 // ---- graph cache for the AR loop
 int g_ar_prune = 1;  // fact_set_flag("ar_prune", 0): run the full last layer (A-B check of the row-0 pruning)
-extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn;
+extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn, g_gemm_finish_ln;
 
 struct GraphKey {
   std::vector<uintptr_t> v;
@@ -462,7 +493,8 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
            reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
            static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(hist_capacity),
            static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers + 1000 * g_ar_prune + 10000 * g_gemm_pair + 100000 * g_gemm_splitk +
-                                  1000000 * g_sdpa_legacy + 10000000 * g_dual_stream + 100000000 * g_gemm_tma_store),
+                                  1000000 * g_sdpa_legacy + 10000000 * g_dual_stream + 100000000 * g_gemm_tma_store +
+                                  1000000000ull * g_gemm_finish_ln),
            static_cast<uintptr_t>(dims->d_model)};
   cudaGraphExec_t exec = nullptr;
   long long frame_kernels = 0;

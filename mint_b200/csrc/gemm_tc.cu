@@ -45,6 +45,10 @@ struct EpiArgs {
   int reduce_add;  // TMA-store epilogue, BIAS_RESID_F32 with out == resid: the add is a bulk reduction in the L2
   float* colsum;   // TMA-store epilogue, GELU_GRAD: += column sums of the staged bf16 box (bias gradient)
   int resid_rows;  // > 0: resid is a [resid_rows, ldr] table read at row % resid_rows (the position embedding)
+  const float* ln_gamma;  // split-K finish: also LayerNorm(out row) -> ln_hi / ln_lo (see fact_gemm_epilogue)
+  const float* ln_beta;
+  bf16* ln_hi;
+  bf16* ln_lo;
 };
 
 template <int BN, int NPART, int STAGES>
@@ -524,6 +528,116 @@ __global__ void __launch_bounds__(256) gemm_finish_kernel(const float* __restric
       ep.out_f32[static_cast<size_t>(map_row(row, ep)) * ep.ldo + col] = x;
     }
   }
+}
+
+// the same, four columns per thread (n, pitches and pointers 16-byte friendly): the batch-1 decode runs 64 of these
+// per frame, so the scalar version's per-element div / mod and 4-byte accesses showed up as 28 % of the frame
+__global__ void __launch_bounds__(256) gemm_finish_vec_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                                              int kind, EpiArgs ep) {
+  const int nv = N >> 2;
+  const long long total4 = static_cast<long long>(M) * nv;
+  const long long slab4 = total4;  // float4 elements per split slab
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += 256ll * gridDim.x) {
+    const int row = static_cast<int>(i / nv), col = static_cast<int>(i % nv) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int zz = 0; zz < splits; ++zz) {
+      const float4 v = reinterpret_cast<const float4*>(part)[zz * slab4 + i];
+      x.x += v.x; x.y += v.y; x.z += v.z; x.w += v.w;
+    }
+    if (kind == FACT_EPI_SPLIT) {
+      if (col + 0 < ep.scale_cols) x.x *= ep.scale;
+      if (col + 1 < ep.scale_cols) x.y *= ep.scale;
+      if (col + 2 < ep.scale_cols) x.z *= ep.scale;
+      if (col + 3 < ep.scale_cols) x.w *= ep.scale;
+    } else if (ep.bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+      x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+    }
+    if (kind == FACT_EPI_BIAS_GELU_SPLIT) {
+      x.x = gelu_tanh(x.x); x.y = gelu_tanh(x.y); x.z = gelu_tanh(x.z); x.w = gelu_tanh(x.w);
+    }
+    if (kind == FACT_EPI_BIAS_RESID_F32) {
+      const float4 r = *reinterpret_cast<const float4*>(ep.resid + resid_row(row, ep) * ep.ldr + col);
+      x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+    }
+    if (kind == FACT_EPI_SPLIT || kind == FACT_EPI_BIAS_GELU_SPLIT) {
+      const uint32_t h0 = cvt_bf16x2(x.x, x.y), h1 = cvt_bf16x2(x.z, x.w);
+      const size_t o = static_cast<size_t>(row) * ep.ldo + col;
+      *reinterpret_cast<uint2*>(ep.out_hi + o) = make_uint2(h0, h1);
+      if (ep.out_lo) {
+        const uint32_t l0 = cvt_bf16x2(x.x - __uint_as_float(h0 << 16), x.y - __uint_as_float(h0 & 0xffff0000u));
+        const uint32_t l1 = cvt_bf16x2(x.z - __uint_as_float(h1 << 16), x.w - __uint_as_float(h1 & 0xffff0000u));
+        *reinterpret_cast<uint2*>(ep.out_lo + o) = make_uint2(l0, l1);
+      }
+    } else {
+      *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(map_row(row, ep)) * ep.ldo + col) = x;
+    }
+  }
+}
+
+// BIAS_RESID_F32 finish fused with the LayerNorm that follows it in a pre-norm layer: one block per row (n <= 1024),
+// thread = one float4 column group, the value stays in registers between the residual write and the normalisation.
+// The reductions reproduce ln_split_kernel's order (per-lane partials over the eight 32-group strides, then the lane
+// butterfly), so the result is bit-identical to running that kernel on the written row.
+__global__ void __launch_bounds__(256) gemm_finish_ln_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                                             EpiArgs ep) {
+  __shared__ float ps[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x, idx = threadIdx.x;
+  const int nv = N >> 2;
+  const bool on = idx < nv;
+  const size_t slab4 = static_cast<size_t>(M) * nv;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) {
+    const float4* p4 = reinterpret_cast<const float4*>(part) + static_cast<size_t>(row) * nv + idx;
+    for (int zz = 0; zz < splits; ++zz) {
+      const float4 t = p4[zz * slab4];
+      x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+    }
+    if (ep.bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias) + idx);
+      x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+    }
+    const float4 r = reinterpret_cast<const float4*>(ep.resid + resid_row(row, ep) * ep.ldr)[idx];
+    x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+    reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(row) * ep.ldo)[idx] = x;
+  }
+  ps[warp][lane] = (x.x + x.y) + (x.z + x.w);
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += ps[i][lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(N);
+  const float a = x.x - mean, b = x.y - mean, c = x.z - mean, e = x.w - mean;
+  __syncthreads();
+  ps[warp][lane] = on ? (a * a + b * b) + (c * c + e * e) : 0.f;
+  __syncthreads();
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q += ps[i][lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(N) + 1e-5f);
+  if (!on) return;
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + idx);
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + idx);
+  float4 y;
+  y.x = (x.x - mean) * rstd * gg.x + bb.x;
+  y.y = (x.y - mean) * rstd * gg.y + bb.y;
+  y.z = (x.z - mean) * rstd * gg.z + bb.z;
+  y.w = (x.w - mean) * rstd * gg.w + bb.w;
+  bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(y.x, h0, l0);
+  split_bf16(y.y, h1, l1);
+  split_bf16(y.z, h2, l2);
+  split_bf16(y.w, h3, l3);
+  reinterpret_cast<uint2*>(ep.ln_hi + static_cast<size_t>(row) * N)[idx] =
+      make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  if (ep.ln_lo)
+    reinterpret_cast<uint2*>(ep.ln_lo + static_cast<size_t>(row) * N)[idx] =
+        make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
 }
 
 // ------------------------------------------------------------------------------------------- CTA-pair variant
@@ -1053,8 +1167,19 @@ static int launch_splitk(const CUtensorMap& a0, const CUtensorMap& a1, const CUt
   kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, kb_per, part);
   FACT_LAUNCH_CHECK("gemm_tc_splitk_kernel launch");
   const long long total = static_cast<long long>(m) * n;
-  int fgrid = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
-  gemm_finish_kernel<<<fgrid, 256, 0, st>>>(part, splits, m, n, kind, ep);
+  if (ep.ln_hi != nullptr) {  // eligibility was checked by the caller (fact_gemm)
+    gemm_finish_ln_kernel<<<m, 256, 0, st>>>(part, splits, m, n, ep);
+    FACT_LAUNCH_CHECK("gemm_finish_ln_kernel launch");
+    return FACT_OK;
+  }
+  if (ep.vec_ok && n % 4 == 0 && ep.ldo % 4 == 0) {  // vec_ok: pitches / pointers allow 16-byte accesses
+    const long long total4 = total / 4;
+    int fgrid = static_cast<int>((total4 + 255) / 256 > 2048 ? 2048 : (total4 + 255) / 256);
+    gemm_finish_vec_kernel<<<fgrid, 256, 0, st>>>(part, splits, m, n, kind, ep);
+  } else {
+    int fgrid = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+    gemm_finish_kernel<<<fgrid, 256, 0, st>>>(part, splits, m, n, kind, ep);
+  }
   FACT_LAUNCH_CHECK("gemm_finish_kernel launch");
   return FACT_OK;
 }
@@ -1141,6 +1266,8 @@ int gemm_tile_n(int n) {
 
 int g_gemm_tma_store = 1;  // fact_set_flag("gemm_tma_store", 0 | 1 | 2): pair-kernel epilogue through bulk tensor stores
                            // (0 = direct row-per-lane stores, 2 = bulk stores but no in-place bulk reduction)
+int g_gemm_finish_ln = 0;  // fact_set_flag("gemm_finish_ln", 1): fuse the LayerNorm into the split-K finish kernel
+                           // (off by default: at batch 1 the separate vectorised finish + LayerNorm measured faster)
 int g_gemm_pair = 1;    // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
 int g_gemm_splitk = 1;  // fact_set_flag("gemm_splitk", 0) disables the small-M split-K path
 
@@ -1160,10 +1287,17 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
 extern "C" int fact_gemm(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
                          int m, int n, int k, const fact_gemm_epilogue* epi, void* stream) {
   FACT_REQUIRE(a_hi && w_hi && epi, FACT_ERR_BAD_SHAPE, "fact_gemm: null operand");
-  bool colsum_fused = false;
+  bool colsum_fused = false;  // also reports a fused LayerNorm (the two options belong to different epilogue kinds)
+  if (epi->ln_hi) {
+    FACT_REQUIRE(epi->kind == FACT_EPI_BIAS_RESID_F32 && epi->seq_in == 0 && epi->ln_gamma && epi->ln_beta &&
+                     epi->ldo == n && n % 4 == 0 && n <= 1024,
+                 FACT_ERR_BAD_SHAPE, "fact_gemm: the LayerNorm option needs BIAS_RESID_F32, no row remap, ldo == n <= 1024");
+  }
   int rc = gemm_dispatch(a_hi, a_lo, lda, w_hi, w_lo, ldw, m, n, k, epi, stream, &colsum_fused);
   if (rc == FACT_OK && epi->kind == FACT_EPI_GELU_GRAD && epi->colsum && !colsum_fused)
     rc = colsum_bf16(epi->out_hi, epi->ldo, epi->colsum, m, n, as_stream(stream));  // kernels without the fused sums
+  if (rc == FACT_OK && epi->ln_hi && !colsum_fused)
+    rc = fact_layernorm_split(epi->out_f32, epi->ln_gamma, epi->ln_beta, epi->ln_hi, epi->ln_lo, m, n, stream);
   return rc;
 }
 
@@ -1204,6 +1338,10 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
   ep.reduce_add = 0;
   ep.colsum = nullptr;
   ep.resid_rows = epi->resid_rows;
+  ep.ln_gamma = nullptr;
+  ep.ln_beta = nullptr;
+  ep.ln_hi = nullptr;
+  ep.ln_lo = nullptr;
   if (split_out)
     ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
                 (!ep.bias || aligned16(ep.bias)) && (!ep.aux || (aligned16(ep.aux) && ep.ldaux % 8 == 0));
@@ -1245,6 +1383,14 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
       const int kb_per = (num_kb + splits - 1) / splits;
       splits = (num_kb + kb_per - 1) / kb_per;
       float* part = static_cast<float*>(epi->splitk_scratch);
+      if (epi->ln_hi && g_gemm_finish_ln && ep.vec_ok && aligned16(epi->ln_gamma) && aligned16(epi->ln_beta) &&
+          (reinterpret_cast<uintptr_t>(epi->ln_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(epi->ln_lo) & 7) == 0) {
+        ep.ln_gamma = epi->ln_gamma;   // the finish kernel normalises the rows it has just written
+        ep.ln_beta = epi->ln_beta;
+        ep.ln_hi = static_cast<bf16*>(epi->ln_hi);
+        ep.ln_lo = static_cast<bf16*>(epi->ln_lo);
+        *colsum_fused = true;
+      }
       if (precise) {
         if (bn == 160) return launch_splitk<160, 2, 3>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);
         if (bn == 256) return launch_splitk<256, 2, 2>(a0, a1, b0, b1, m, n, k, splits, kb_per, epi->kind, ep, part, st);

@@ -270,6 +270,7 @@ extern int g_gemm_splitk;
 extern int g_gemm_bn;
 extern int g_gemm_tma_store;
 extern int g_wgrad_pair;
+extern int g_gemm_finish_ln;
 extern int g_sdpa_bwd_tc;
 extern int g_dual_stream;
 extern int g_ar_prune;
@@ -298,6 +299,10 @@ extern "C" int fact_set_flag(const char* name, int value) {
   }
   if (name && strcmp(name, "sdpa_bwd_tc") == 0) {
     g_sdpa_bwd_tc = value;
+    return FACT_OK;
+  }
+  if (name && strcmp(name, "gemm_finish_ln") == 0) {
+    g_gemm_finish_ln = value;
     return FACT_OK;
   }
   if (name && strcmp(name, "wgrad_pair") == 0) {

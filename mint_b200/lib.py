@@ -57,7 +57,8 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("kind", _i), ("out_f32", _vp), ("out_hi", _vp), ("out_lo", _vp), ("ldo", _i), ("bias", _vp),
                 ("resid", _vp), ("ldr", _i), ("scale", _f), ("scale_cols", _i), ("seq_in", _i), ("seq_out", _i),
                 ("seq_off", _i), ("aux", _vp), ("ldaux", _i), ("splitk_scratch", _vp), ("splitk_scratch_bytes", C.c_size_t),
-                ("colsum", _vp), ("resid_rows", _i)]
+                ("colsum", _vp), ("resid_rows", _i),
+                ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_hi", _vp), ("ln_lo", _vp)]
 
 
 # symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/fact_sm100.h

@@ -285,6 +285,58 @@ def test_gemm_embedding_shape_broadcast_residual(fact_lib, cuda, m, seq, pair, p
     assert rel_err(out.double(), ref) < 3e-5
 
 
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("m,n,k,pitch_rows", [(360, 800, 800, 1), (360, 800, 3072, 1), (128, 800, 800, 360),
+                                              (5000, 800, 800, 1)])
+def test_gemm_residual_with_layernorm(fact_lib, cuda, m, n, k, pitch_rows, precise):
+    """BIAS_RESID_F32 with the LayerNorm option: x += a.W^T + b in place, then LayerNorm(x) split to hi / lo.  Small m
+    takes the split-K finish kernel with the normalisation fused (flag 1) -- bit-identical to the separate LayerNorm
+    launch (flag 0) and to the large-m path, and right against torch.  pitch_rows > 1: operand / residual rows taken
+    every pitch_rows-th row (the row-0 tail of the AR step)."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    a_full = torch.randn(m * pitch_rows, k, generator=g).to(cuda)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda)
+    bias = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    gamma = (1 + 0.1 * torch.randn(n, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    x0 = torch.randn(m * pitch_rows, n, generator=g).to(cuda)
+    a_hi, a_lo = split_ref(a_full)
+    w_hi, w_lo = split_ref(w)
+    scratch = torch.full((16 * min(m, 1024) * n,), float("nan"), device=cuda)
+    results = []
+    for flag in (1, 0):
+        fact_lib.fact_set_flag(b"gemm_finish_ln", flag)
+        inplace = pitch_rows == 1
+        x = x0.clone()
+        out = x if inplace else torch.full((m, n), float("nan"), device=cuda)
+        ln_hi = torch.zeros(m, n, dtype=torch.bfloat16, device=cuda)
+        ln_lo = torch.zeros_like(ln_hi)
+        e = _epi(kind=L.EPI_BIAS_RESID_F32, out_f32=out, ldo=n, bias=bias, resid=x, ldr=n * pitch_rows,
+                 ln_gamma=gamma, ln_beta=beta, ln_hi=ln_hi)
+        if precise:
+            e.ln_lo = ln_lo.data_ptr()
+        e.splitk_scratch, e.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
+        try:
+            L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, k * pitch_rows,
+                                       w_hi.data_ptr(), w_lo.data_ptr() if precise else None, k, m, n, k, C.byref(e),
+                                       _st()))
+            torch.cuda.synchronize()
+        finally:
+            fact_lib.fact_set_flag(b"gemm_finish_ln", 0)
+        results.append((out.clone(), ln_hi.clone(), ln_lo.clone()))
+    for t0, t1 in zip(*results):
+        assert torch.equal(t0, t1)
+    out, ln_hi, ln_lo = results[0]
+    rows = slice(None, None, pitch_rows)
+    a_eff = (join(a_hi, a_lo) if precise else a_hi.float()).double()[rows]
+    w_eff = (join(w_hi, w_lo) if precise else w_hi.float()).double()
+    ref = a_eff @ w_eff.t() + bias.double() + x0.double()[rows]
+    assert rel_err(out.double(), ref) < 3e-5
+    ln_ref = torch.nn.functional.layer_norm(out.double(), (n,), gamma.double(), beta.double(), 1e-5)
+    got = (join(ln_hi, ln_lo) if precise else ln_hi.float()).double()
+    assert rel_err(got, ln_ref) < (3e-5 if precise else 4e-3)
+
+
 def test_gemm_tc_inplace_residual(fact_lib, cuda):
     """out-proj / FF2 write the residual stream in place (out == resid)."""
     m, n, k = 360, 800, 800
