@@ -1266,8 +1266,8 @@ int gemm_tile_n(int n) {
 
 int g_gemm_tma_store = 1;  // fact_set_flag("gemm_tma_store", 0 | 1 | 2): pair-kernel epilogue through bulk tensor stores
                            // (0 = direct row-per-lane stores, 2 = bulk stores but no in-place bulk reduction)
-int g_gemm_finish_ln = 0;  // fact_set_flag("gemm_finish_ln", 1): fuse the LayerNorm into the split-K finish kernel
-                           // (off by default: at batch 1 the separate vectorised finish + LayerNorm measured faster)
+int g_gemm_finish_ln = 1;  // fact_set_flag("gemm_finish_ln", 0): keep the LayerNorm out of the split-K finish kernel
+                           // (batch 1: 722 frames/s fused, block per row, vs 656 with a separate LayerNorm launch)
 int g_gemm_pair = 1;    // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
 int g_gemm_splitk = 1;  // fact_set_flag("gemm_splitk", 0) disables the small-M split-K path
 
