@@ -42,6 +42,36 @@ def test_abi_version_and_error_string(fact_lib):
     assert fact_lib.fact_workspace_bytes(ctypes.byref(d), 128, L.MODE_BF16) < need
 
 
+def test_ctypes_structs_match_the_c_layout(tmp_path):
+    """The header is plain C (gcc, no CUDA headers) and every struct the ctypes layer mirrors has the same size and
+    field offsets as the C compiler gives it -- a silent mismatch would corrupt pointers across the boundary."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    structs = {"fact_gemm_epilogue": L.GemmEpilogue, "fact_dims": L.Dims, "fact_layer_weights": L.LayerWeights,
+               "fact_weights": L.Weights, "fact_layer_grads": L.LayerGrads, "fact_grads": L.Grads}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, what, value = line.split()
+        ct = structs[cname]
+        expect = ctypes.sizeof(ct) if what == "size" else getattr(ct, what).offset
+        assert int(value) == expect, f"{cname}.{what}: C {value} != ctypes {expect}"
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, "_lib", None)
     monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
