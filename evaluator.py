@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--model_dir", default="/tmp/fact_b200")
     ap.add_argument("--output_dir", default="outputs")
     ap.add_argument("--data_npz", default="")
+    ap.add_argument("--tf_checkpoint", default="", help="TensorFlow checkpoint prefix (ckpt-N) to evaluate; default: "
+                    "the newest TF checkpoint in --model_dir if there is one, else the newest ckpt-*.pt")
     ap.add_argument("--num_clips", type=int, default=4)
     ap.add_argument("--steps", type=int, default=1200)
     ap.add_argument("--mode", default="precise", choices=["precise", "bf16"])
@@ -40,8 +42,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = config_util.get_configs_from_pipeline_file(args.config_path)
     model = model_builder.build(cfg["model"], True, device=dev, mode=args.mode)      # is_training=True: evaluator.py:56
-    ckpts = sorted(f for f in os.listdir(args.model_dir) if f.startswith("ckpt-")) if os.path.isdir(args.model_dir) else []
-    if ckpts:
+    from mint_b200 import tf_checkpoint
+    tf_prefix = args.tf_checkpoint or tf_checkpoint.latest_checkpoint(args.model_dir)   # evaluator.py:56-60 restores TF
+    ckpts = sorted(f for f in os.listdir(args.model_dir) if f.startswith("ckpt-") and f.endswith(".pt")) \
+        if os.path.isdir(args.model_dir) else []
+    if tf_prefix:
+        model.set_weights(tf_checkpoint.load_fact_weights(tf_prefix, model.dims))
+    elif ckpts:
         sd = torch.load(os.path.join(args.model_dir, ckpts[-1]), map_location=dev)
         model.flat_parameters.copy_(sd["flat_parameters"])
         model.repack()

@@ -52,6 +52,10 @@ def main():
     ap.add_argument("--steps_per_loop", type=int, default=10)          # trainer.py:166
     ap.add_argument("--checkpoint_interval", type=int, default=1000)   # trainer.py:170
     ap.add_argument("--max_to_keep", type=int, default=5)
+    ap.add_argument("--init_tf_checkpoint", default="", help="TensorFlow checkpoint prefix to start from (weights only)")
+    ap.add_argument("--export_tf_checkpoint", action="store_true",
+                    help="also write every checkpoint in TensorFlow's format (ckpt-N.index / .data), readable by the "
+                         "reference's tf.train.Checkpoint(model=...)")
     ap.add_argument("--data_npz", default="")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -76,6 +80,9 @@ def main():
     trainer = SingleTaskTrainer(data, "target", model, optimizer=opt, grad_clip_norm=args.grad_clip_norm)
     os.makedirs(args.model_dir, exist_ok=True)
     ckpts = sorted(f for f in os.listdir(args.model_dir) if f.startswith("ckpt-") and f.endswith(".pt"))
+    if args.init_tf_checkpoint and not ckpts:
+        from mint_b200 import tf_checkpoint
+        model.set_weights(tf_checkpoint.load_fact_weights(args.init_tf_checkpoint, model.dims))
     if ckpts:                                                               # Controller restores the latest (orbit)
         sd = torch.load(os.path.join(args.model_dir, ckpts[-1]), map_location=dev)
         model.flat_parameters.copy_(sd["flat_parameters"])
@@ -91,7 +98,13 @@ def main():
                     path = os.path.join(args.model_dir, "ckpt-%09d.pt" % opt.iterations)
                     torch.save({"flat_parameters": model.flat_parameters, "optimizer": opt.state_dict(),
                                 "names": model.variable_names()}, path)
-                    old = sorted(f for f in os.listdir(args.model_dir) if f.startswith("ckpt-"))[:-args.max_to_keep]
+                    if args.export_tf_checkpoint:
+                        from mint_b200 import tf_checkpoint
+                        tf_checkpoint.save_fact_weights(os.path.join(args.model_dir, "ckpt-%d" % opt.iterations),
+                                                        {n: v.cpu().numpy() for n, v in model.get_weights().items()},
+                                                        model.dims, step=opt.iterations)
+                    old = sorted(f for f in os.listdir(args.model_dir)
+                                 if f.startswith("ckpt-") and f.endswith(".pt"))[:-args.max_to_keep]
                     for f in old:
                         os.remove(os.path.join(args.model_dir, f))
     if world > 1:
