@@ -9,6 +9,7 @@ below carry their documented Keras semantics in float64:
   Dense: x @ kernel + bias, kernel [in, units] glorot-uniform, bias zeros, optional activation / kernel_initializer
   LayerNormalization(epsilon): last axis, biased variance, gamma ones / beta zeros
   Sequential, Model/Layer (__call__ -> call), add_weight, einsum, nn.softmax, tanh, pow, concat, reduce_mean, square
+  pad, maximum, random.uniform, Tensor.set_shape (checked) for mint/utils/inputs_util.py (tests/golden/make_inputs_golden.py)
 Nothing here is used by the product or shipped to the GPU box.
 """
 import math
@@ -40,6 +41,13 @@ class Tensor(np.ndarray):
     @property
     def shape(self):
         return _Shape(np.ndarray.shape.__get__(self))
+
+
+    def set_shape(self, shape):  # static-shape annotation in TF; here: check it (inputs_util.py:88-103)
+        want = tuple(shape)
+        got = tuple(np.ndarray.shape.__get__(self))
+        if len(want) != len(got) or any(w is not None and int(w) != g for w, g in zip(want, got)):
+            raise ValueError(f"set_shape{want} on a tensor of shape {got}")
 
 
 class Variable(Tensor):  # einops probes tf.Tensor / tf.Variable when a module named tensorflow is loaded
@@ -90,6 +98,27 @@ def _softmax(x, axis=-1):
     e = np.exp(x - x.max(axis=axis, keepdims=True))
     return _t(e / e.sum(axis=axis, keepdims=True))
 
+
+# ---- the primitives of mint/utils/inputs_util.py:59-107 (fact_preprocessing), dtype-preserving
+def pad(x, paddings):
+    a = np.asarray(x)
+    return np.pad(a, [[int(p[0]), int(p[1])] for p in paddings]).view(Tensor)
+
+
+def maximum(a, b):
+    return np.maximum(a, b)
+
+
+def _random_uniform(shape, minval=0, maxval=None, dtype=None):
+    """tf.random.uniform for the one call the reference makes: a scalar int32 in [minval, maxval).  `FORCED_START`
+    (set by the golden generator) replaces the draw so that both implementations slice the same window."""
+    if FORCED_START is not None:
+        return np.int32(FORCED_START)
+    return np.int32(_RNG.integers(int(minval), int(maxval)))
+
+
+FORCED_START = None
+random = types.SimpleNamespace(uniform=_random_uniform)
 
 nn = types.SimpleNamespace(softmax=_softmax, relu=lambda x: _t(np.maximum(np.asarray(x), 0)))
 

@@ -90,3 +90,41 @@ def test_create_input_train_and_eval(tmp_path):
     ev = list(inputs.create_input(cfg["eval_config"], cfg["eval_dataset"], is_training=False))
     assert [e["audio_input"].shape for e in ev] == [(1, 300, 35), (1, 280, 35), (1, 290, 35)]   # ordered, batch 1
     assert ev[0]["motion_input"].shape == (1, 120, 225)
+
+
+def test_fact_preprocessing_matches_the_references_own_code():
+    """tests/golden/inputs_reference.npz: outputs of the reference's mint/utils/inputs_util.py (run over the TF shim)
+    on a self-describing sequence, for forced window starts and for eval; the parameter dict comes from the
+    reference's get_modality_to_param_dict on its pipeline_pb2 parse of the fact_v5 config."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs_reference.npz"))
+    ref_params = json.loads(bytes(g["params_json"]).decode())
+    cfg = config_util.get_configs_from_pipeline_file(config_util.DEFAULT_CONFIG)
+    params = inputs.get_modality_to_param_dict(cfg["train_dataset"])
+    for mod in ("motion", "audio"):
+        for k in ("feature_dim", "input_length", "target_length", "target_shift"):
+            assert params[mod][k] == ref_params[mod][k], (mod, k)
+    seq, audio = g["motion_sequence"], g["audio_sequence"]
+    lo, hi = g["uniform_bounds"][0]
+
+    class Forced:
+        def __init__(self, start):
+            self.start, self.calls = start, []
+
+        def integers(self, a, b=None):
+            self.calls.append((a, b))
+            return self.start
+
+    for i, start in enumerate(g["starts"]):
+        rng = Forced(int(start))
+        ex = inputs.fact_preprocessing({"motion_sequence": seq, "audio_sequence": audio}, params, True, rng)
+        assert rng.calls == [(int(lo), int(hi))]              # same draw range as tf.random.uniform([], 0, T - 240 + 1)
+        for k in ("motion_input", "target", "audio_input"):
+            assert ex[k].dtype == g[f"train{i}_{k}"].dtype
+            np.testing.assert_array_equal(ex[k], g[f"train{i}_{k}"])
+        assert "motion_sequence" not in ex and "audio_sequence" not in ex
+    ev = inputs.fact_preprocessing({"motion_sequence": seq, "audio_sequence": audio}, params, False)
+    np.testing.assert_array_equal(ev["motion_input"], g["eval_motion_input"])
+    np.testing.assert_array_equal(ev["audio_input"], g["eval_audio_input"])
+    assert "target" not in ev
