@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / fast-mode legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg only")
     ap.add_argument("--cpu-frames", dest="cpu_frames", type=int, default=120,
-                    help="AR frames per clip of the bounded cpu_baseline sample (~10 s at 15 frames/s)")
+                    help="upper bound on the AR frames per clip of the cpu_baseline sample (the sample is sized to "
+                         "~12 s of CPU work at the calibrated rate)")
     ap.add_argument("--kernels-only", action="store_true", help="developer aid: time the hot kernels alone and exit")
     ap.add_argument("--flag", action="append", default=[], help="developer aid: fact_set_flag name=value")
     return ap.parse_args()
@@ -133,7 +134,7 @@ def _cpu_worker(idx, threads, steps, warmup, q, batch=1):
     q.put(("done", idx, t_total))
 
 
-def cpu_frames_per_sec(steps, warmup, procs=1, threads=None):
+def cpu_frames_per_sec(steps, warmup, procs=1, threads=None, target_seconds=None):
     """Torch-CPU fp32 restatement of the reference math on the host cores, AR generation.
 
     Measured on the GPU box (Xeon 8562Y+, 128 hardware threads): one process is fastest at 16 intra-op threads (67 ms
@@ -164,6 +165,8 @@ def cpu_frames_per_sec(steps, warmup, procs=1, threads=None):
                 best = (b / dt, cand, b)
         threads, batch = best[1], best[2]
         del w
+        if target_seconds:  # bounded sample: as many AR frames per clip as fit the time budget at the calibrated rate
+            steps = max(4, min(steps, int(round(target_seconds * best[0] / batch))))
     if procs == 1:
         import queue
         q = queue.Queue()
@@ -462,7 +465,7 @@ def run_ours(args):
         line.update(extras)
         if world == 1 and not args.no_extras and not args.no_cpu:
             try:
-                cpu_fps, cpu_total, threads, desc = cpu_frames_per_sec(args.cpu_frames, 2)
+                cpu_fps, cpu_total, threads, desc = cpu_frames_per_sec(args.cpu_frames, 2, target_seconds=12.0)
                 line["cpu_baseline"] = {
                     "value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
                     "sample": f"{desc}; torch-CPU fp32 restatement (TensorFlow absent), {cpu_total:.1f} s"}
