@@ -15,7 +15,8 @@ this module reads and writes the format itself (host-side, NumPy):
 
 Pinning: the table / entry / tensor layer is checked against a REAL TensorFlow-written bundle that ships inside the
 reference tree (third_party/tf_models/research/lfads/synth_data/trained_itb/model-65000.*: every block and tensor
-checksum verifies, tests/test_tf_checkpoint.py; a committed copy of its 266-byte index is the golden).  That file is a
+checksum verifies and the writer reproduces its `.index` and `.data` files byte for byte -- the committed golden is
+the decoded tensors plus TensorFlow's file hashes, tests/golden/make_tf_bundle_golden.py).  That file is a
 TF1 Saver bundle without an object graph, so the object-graph message numbers and the string-tensor framing below
 follow the published TensorFlow sources from memory and are exercised only by this module's own writer:
 **object-graph layer unpinned**.

@@ -1,5 +1,6 @@
 """mint_b200/tf_checkpoint.py: the TensorBundle layer against a checkpoint written by TensorFlow
-itself (tests/golden/tf_bundle), and the FACT variable mapping / object graph through a write-read round trip."""
+itself (its decoded tensors + file hashes: tests/golden/tf_bundle_*), and the FACT variable mapping / object graph
+through a write-read round trip."""
 import hashlib
 import json
 import os
@@ -15,48 +16,54 @@ from tests.helpers import make_config
 def _dims(**kw):
     return config_util.resolve_fact_dims(make_config(**kw))
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_bundle")
-PREFIX = os.path.join(GOLD, "model-65000")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MANIFEST = json.load(open(os.path.join(GOLD, "tf_bundle_manifest.json")))
 
 
-def test_golden_files_are_the_ones_tensorflow_wrote():
-    manifest = json.load(open(os.path.join(GOLD, "MANIFEST.json")))
-    for name, digest in manifest["files"].items():
-        assert hashlib.sha256(open(os.path.join(GOLD, name), "rb").read()).hexdigest() == digest
+@pytest.fixture()
+def tf_written(tmp_path):
+    """A bundle written by THIS repo's writer from the decoded tensors of a TensorFlow-written checkpoint; both files
+    must hash to what TensorFlow wrote (tests/golden/make_tf_bundle_golden.py), so everything read back from it is read
+    from TensorFlow's own bytes."""
+    tensors = np.load(os.path.join(GOLD, "tf_bundle_tensors.npz"))
+    prefix = str(tmp_path / "model-65000")
+    w = T.BundleWriter(prefix)
+    for k in tensors.files:
+        w.add(k, tensors[k])
+    w.close()
+    for ext, meta in MANIFEST["files"].items():
+        raw = open(prefix + ext, "rb").read()
+        assert len(raw) == meta["bytes"], ext
+        assert hashlib.sha256(raw).hexdigest() == meta["sha256"], f"{ext}: not byte-identical to TensorFlow's file"
+    return prefix
 
 
-def test_reads_a_tensorflow_written_bundle_with_every_checksum_verified():
-    b = T.Bundle(PREFIX, verify_table=True)
-    assert b.num_shards == 1
-    assert b.keys() == ["Variable", "Variable_1", "Variable_2", "Variable_3", "Variable_4", "global_step"]
-    shapes = {k: b.entries[k].shape for k in b.keys()}
-    assert shapes == {"Variable": (50, 50), "Variable_1": (1, 50), "Variable_2": (1, 50), "Variable_3": (50, 1),
-                      "Variable_4": (1,), "global_step": ()}
+def test_writer_reproduces_tensorflows_bytes(tf_written):
+    assert os.path.getsize(tf_written + ".index") == 266
+
+
+def test_reads_tensorflows_bytes_with_every_checksum_verified(tf_written):
+    b = T.Bundle(tf_written, verify_table=True)
+    assert b.num_shards == MANIFEST["num_shards"] == 1
+    assert b.keys() == sorted(MANIFEST["entries"])
+    for k, want in MANIFEST["entries"].items():       # the entry table TensorFlow wrote (decoded in the build container)
+        e = b.entries[k]
+        assert (e.dtype, list(e.shape), e.offset, e.size, e.crc) == \
+            (want["dtype"], want["shape"], want["offset"], want["size"], want["masked_crc32c"]), k
     step = b.tensor("global_step", verify=True)
-    assert step.dtype == np.int32 and step.shape == () and int(step) == 65000      # the file is model-65000
+    assert step.dtype == np.int32 and step.shape == () and int(step) == 65000      # the checkpoint is model-65000
     w = b.tensor("Variable", verify=True)
-    assert w.dtype == np.float32 and np.isfinite(w).all() and 0.01 < float(np.abs(w).mean()) < 1.0
-    # offsets tile the data file exactly
-    end = 0
+    assert w.dtype == np.float32 and w.shape == (50, 50) and np.isfinite(w).all()
+    end = 0                                                                        # offsets tile the data file exactly
     for k in sorted(b.keys(), key=lambda k: b.entries[k].offset):
         assert b.entries[k].offset == end
         end += b.entries[k].size
-    assert end == os.path.getsize(PREFIX + ".data-00000-of-00001")
+    assert end == os.path.getsize(tf_written + ".data-00000-of-00001")
 
 
-def test_writer_reproduces_tensorflows_bytes(tmp_path):
-    b = T.Bundle(PREFIX)
-    w = T.BundleWriter(str(tmp_path / "copy"))
-    for k in b.keys():
-        w.add(k, b.tensor(k))
-    w.close()
+def test_corruption_is_detected(tf_written, tmp_path):
     for ext in (".index", ".data-00000-of-00001"):
-        assert open(str(tmp_path / "copy") + ext, "rb").read() == open(PREFIX + ext, "rb").read(), ext
-
-
-def test_corruption_is_detected(tmp_path):
-    for ext in (".index", ".data-00000-of-00001"):
-        shutil.copyfile(PREFIX + ext, str(tmp_path / "m") + ext)
+        shutil.copyfile(tf_written + ext, str(tmp_path / "m") + ext)
     data = bytearray(open(str(tmp_path / "m.data-00000-of-00001"), "rb").read())
     data[123] ^= 0x40
     open(str(tmp_path / "m.data-00000-of-00001"), "wb").write(bytes(data))
