@@ -47,6 +47,13 @@ def parse():
     ap.add_argument("--cpu-frames", dest="cpu_frames", type=int, default=120,
                     help="upper bound on the AR frames per clip of the cpu_baseline sample (the sample is sized to "
                          "~12 s of CPU work at the calibrated rate)")
+    ap.add_argument("--train-batch", dest="train_batch", type=int, default=128,
+                    help="clips per GPU of the training leg (BASELINE.json configs[2]/[3])")
+    ap.add_argument("--no-train", action="store_true", help="skip the data-parallel training leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1->512 sweep leg (configs[4])")
+    ap.add_argument("--sweep", default="1,2,4,8,16,32,64,128,256,512", help="clips per GPU of the sweep leg")
+    ap.add_argument("--b1-frames", dest="b1_frames", type=int, default=1200,
+                    help="frames of the single-clip leg (configs[1]: 1200 = 20 s at 60 fps)")
     ap.add_argument("--kernels-only", action="store_true", help="developer aid: time the hot kernels alone and exit")
     ap.add_argument("--flag", action="append", default=[], help="developer aid: fact_set_flag name=value")
     return ap.parse_args()
@@ -294,9 +301,191 @@ def kernel_rooflines(model, batch, mode, peaks, stream):
     # fused attention block as the metric defines it: x in + y out + weights, nothing else
     t_blk = res["layernorm_split"]["s"] + res["gemm_qkv"]["s"] + res["sdpa"]["s"] + res["gemm_out"]["s"]
     blk_bytes = 1600.0 * batch * n_seq * 4 + 2562400.0 * s_el
-    res["attn_block"] = {"s": t_blk, "gbs": blk_bytes / t_blk / 1e9, "frac_hbm": blk_bytes / t_blk / 1e9 / peaks["hbm_gbs"]}
+    blk_flops = mult * (2.0 * M * 3 * d * d + 2.0 * M * d * d + 3200.0 * n_seq * n_seq * batch)
+    blk_bytes_s2 = 1600.0 * batch * n_seq * 2 + 2562400.0 * 2
+    res["attn_block"] = {"s": t_blk, "gbs": blk_bytes / t_blk / 1e9, "frac_hbm": blk_bytes / t_blk / 1e9 / peaks["hbm_gbs"],
+                         "s_el": 4, "frac_hbm_s2": blk_bytes_s2 / t_blk / 1e9 / peaks["hbm_gbs"],
+                         "executed_tflops": blk_flops / t_blk / 1e12}
     return res
 
+
+
+# --------------------------------------------------------------------------------------------- training leg
+TRAIN_FLOP_PER_CLIP = 3 * FLOP_PER_FRAME   # forward + backward (2x forward) of one clip, SURVEY.md 8(a) a14
+
+
+def time_wgrad(model, batch, stream):
+    """gemm_wgrad2_kernel alone at the FFN shape of a B-clip step: dW1[800, 3072] += ln2[M, 800]^T . dz[M, 3072]."""
+    import torch
+    from mint_b200 import lib as L
+    lib = L.load()
+    d, ff = model.dims.cross_hidden, model.dims.cross_ff
+    M = batch * model.dims.cross_seq
+    dev = model.device
+    x = (torch.randn(M, d, device=dev) * 0.05).to(torch.bfloat16)
+    dy = (torch.randn(M, ff, device=dev) * 0.05).to(torch.bfloat16)
+    dw = torch.zeros(d, ff, device=dev)
+    st = stream.cuda_stream
+
+    def run():
+        L.check(lib.fact_wgrad_gemm(x.data_ptr(), d, dy.data_ptr(), ff, dw.data_ptr(), ff, M, d, ff, st),
+                "fact_wgrad_gemm")
+    t = time_kernel(run, stream)
+    return t, 2.0 * M * d * ff
+
+
+def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, max_over_ranks):
+    """BASELINE.json configs[2] (N=1) / configs[3] (N>1): one sync data-parallel training step per "step" --
+    fact_train_step (forward with saved activations, L2 motion loss, full backward), ONE logical all-reduce of the
+    flat fp32 gradient bucket (three slices, the first two overlapped with the backward), Keras Adam.
+    Reference: mint/ctl/single_task_trainer.py:138-199, trainer.py:125-135."""
+    import torch
+    import torch.distributed as dist
+    from mint_b200 import lib as L, model_builder, optim
+    from mint_b200.trainer import SingleTaskTrainer
+
+    B, K, Wm = args.train_batch, args.steps, max(args.warmup, 3)
+    model = model_builder.build(cfg["model"], is_training=True, device=dev, mode="bf16", seed=0)
+    d = model.dims
+    opt = optim.Adam(model, learning_rate=optim.learning_rate_from_config(cfg["train_config"]))
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    host = {"motion_input": (0.5 * torch.randn(B, d.motion.seq_len, d.motion.feature_dim, generator=g)).pin_memory(),
+            "audio_input": torch.randn(B, d.audio.seq_len, d.audio.feature_dim, generator=g).pin_memory(),
+            "target": (0.5 * torch.randn(B, 20, d.out_dim, generator=g)).pin_memory()}
+    out = {"config": {"workload": "fact_v5_deeper_t10_cm12 training step", "batch_per_gpu": B,
+                      "global_batch": B * world, "products": "bf16 (fp32 accumulate, fp32 master weights / Adam state)",
+                      "loss": "L2 motion loss on the first 20 frames", "optimizer": "Keras Adam",
+                      "parallelism": f"dp{world}: one all-reduce of the flat fp32 gradient bucket per step, issued as "
+                                     "3 slices (cross stack+head, motion encoder, audio encoder); the first two overlap "
+                                     "the rest of the backward on a side stream" if world > 1 else "single GPU"}}
+    with torch.cuda.stream(stream):
+        batch_d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        dp = SingleTaskTrainer([], "target", model, optimizer=opt)
+        local_only = SingleTaskTrainer([], "target", model, optimizer=opt, allreduce=False)
+        losses = [dp.train_step(batch_d) for _ in range(Wm)]
+        first_loss = float(losses[0])
+        barrier()
+
+        def timed(fn, steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(steps):
+                last = fn()
+            e1.record(stream)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / steps, t0, time.perf_counter(), last
+
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        launches0 = L.load().fact_launch_count()
+        ms, t0, t1, last = timed(lambda: dp.train_step(batch_d), K)
+        launches = L.load().fact_launch_count() - launches0
+        clocks = sampler.stop(t0, t1) if rank == 0 else None
+        ar_ms = exposed = ms_local = None
+        if world > 1:
+            ms_local, _, _, _ = timed(lambda: local_only.train_step(batch_d), K)
+            ms2, _, _, _ = timed(lambda: dp.train_step(batch_d), K)     # again, so both sides see the same clocks
+            ms_dp = min(ms, ms2)
+            exposed = ms_dp - ms_local
+            grads = model.flat_gradients
+
+            def ar():
+                dist.all_reduce(grads)
+            ar_ms, _, _, _ = timed(ar, 5)
+        # end to end: pinned host batch -> device inside the step, loss read back to pinned host memory every step
+        loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
+        step_i = [0]
+
+        def e2e_step():
+            bd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            loss = dp.train_step(bd)
+            loss_host[step_i[0] % K].copy_(loss, non_blocking=True)
+            step_i[0] += 1
+            return loss
+        e2e_step()
+        barrier()
+        tw0 = time.perf_counter()
+        for _ in range(K):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_ms = max_over_ranks((time.perf_counter() - tw0) * 1e3) / K
+        barrier()
+        assert torch.isfinite(loss_host).all(), "non-finite training loss"
+        wg = None
+        if rank == 0:
+            try:
+                t_w, fl = time_wgrad(model, B, stream)
+                wg = {"bound": "tensor", "kernel": f"gemm_wgrad2_kernel (dW1: tokens={B * d.cross_seq}, 800x3072, "
+                                                   "tcgen05 cta_group::2, MN-major operands)",
+                      "achieved": fl / t_w / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                      "frac": fl / t_w / 1e12 / peaks["bf16_tflops"], "us_per_launch": t_w * 1e6,
+                      "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
+            except Exception as exc:
+                wg = {"error": repr(exc)[:300]}
+    h2d = sum(v.numel() for v in host.values()) * 4
+    out.update({
+        "ms_per_step": ms, "samples_per_s": world * B * 1e3 / ms, "steps": K, "warmup": Wm,
+        "algorithmic_tflops_per_gpu": TRAIN_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12,
+        "frac_of_sustained_tensor_peak": TRAIN_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+        "allreduce_ms": ar_ms, "exposed_allreduce_ms": exposed, "ms_per_step_without_allreduce": ms_local,
+        "grad_bucket_mb": model.flat_gradients.numel() * 4 / 1e6,
+        "e2e": {"ms_per_step": e2e_ms, "samples_per_s": world * B * 1e3 / e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches_per_step": int(launches) // K, "loss_first": first_loss, "loss_last": float(last),
+        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "roofline": wg, "clocks": clocks,
+        "scaling": "weak"})
+    del dp, local_only, opt, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sweep_leg(args, model, dev, world, rank, stream, barrier, max_over_ranks, peaks):
+    """BASELINE.json configs[4]: AR frames/s at B clips per GPU, B = 1 .. 512, every rank generating its own clips
+    (weak scaling, no data-path collective); the attention core's HBM fraction per point on rank 0."""
+    import torch
+    from mint_b200 import lib as L
+    lib = L.load()
+    dims = model.dims
+    H, d, ns = dims.cross_heads, dims.cross_hidden, dims.cross_seq
+    precise = model.mode == "precise"
+    pts = []
+    for B in [int(v) for v in args.sweep.split(",") if v]:
+        k = max(4, min(args.steps, 12 if B <= 128 else 6))
+        w = 3
+        T = dims.audio.seq_len + w + k - 1
+        motion = 0.5 * torch.randn(B, dims.motion.seq_len, dims.motion.feature_dim, device=dev)
+        motion[..., :6] = 0
+        audio = torch.randn(B, T, dims.audio.feature_dim, device=dev)
+        hist = model.new_history(motion, w + k)
+        model.generate_into(hist, audio, 0, w)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        model.generate_into(hist, audio, w, k)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / k
+        pt = {"batch_per_gpu": B, "frames_per_s": world * B * 1e3 / ms, "ms_per_step": ms, "frames_timed": k}
+        if rank == 0:
+            M = B * ns
+            qkv = [(torch.randn(M, 3 * d, device=dev) * 0.05).to(torch.bfloat16) for _ in range(2 if precise else 1)]
+            ao = [torch.empty(M, d, dtype=torch.bfloat16, device=dev) for _ in range(2 if precise else 1)]
+
+            def sdpa():
+                L.check(lib.fact_sdpa(qkv[0].data_ptr(), qkv[-1].data_ptr() if precise else None, ao[0].data_ptr(),
+                                      ao[-1].data_ptr() if precise else None, B, ns, H, d // H, stream.cuda_stream))
+            t = time_kernel(sdpa, stream, iters=4, warm=2)
+            byts = 4.0 * M * d * (4 if precise else 2)
+            pt["sdpa_core_gbs"] = byts / t / 1e9
+            pt["sdpa_core_frac_hbm"] = byts / t / 1e9 / peaks["hbm_gbs"]
+            del qkv, ao
+        pts.append(pt)
+        del hist, audio, motion
+    return pts
 
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
@@ -394,21 +583,39 @@ def run_ours(args):
         extras = {}
         if rank == 0 and not args.no_extras and world == 1:
           try:
-            # BASELINE.json configs[1]: one clip (batch 1), same model / mode, device-resident
-            n1 = Wm + 4 * K
-            m1 = motion_d[:1].contiguous()
-            a1w = torch.randn(1, dims.audio.seq_len + n1 - 1, dims.audio.feature_dim, device=dev)
-            h1 = model.new_history(m1, n1)
-            model.generate_into(h1, a1w, 0, Wm)
+            # BASELINE.json configs[1]: ONE clip, 1200 frames (20 s at 60 fps), T = 1439 audio frames, same model / mode.
+            # Device-resident leg (frames appended to a resident history) and the public-API leg
+            # (FACTModel.infer_auto_regressive: pinned host inputs -> host frames, copies inside the timed region).
+            n1 = max(8, args.b1_frames)
+            g1 = torch.Generator(device="cpu").manual_seed(7)
+            m1_h = motion_h[:1].clone().pin_memory()
+            a1_h = torch.randn(1, dims.audio.seq_len + n1 - 1, dims.audio.feature_dim, generator=g1).pin_memory()
+            m1, a1w = m1_h.to(dev), a1_h.to(dev)
+            h1 = model.new_history(m1, n1 + Wm)
+            a1pad = torch.cat([a1w, torch.randn(1, Wm, dims.audio.feature_dim, device=dev)], dim=1)
+            model.generate_into(h1, a1pad, 0, Wm)
             stream.synchronize()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record(stream)
-            model.generate_into(h1, a1w, Wm, 4 * K)
+            model.generate_into(h1, a1pad, Wm, n1)
             f1.record(stream)
             stream.synchronize()
-            ms1 = f0.elapsed_time(f1) / (4 * K)
-            extras["batch1"] = {"value": 1e3 / ms1, "unit": "frames/s", "ms_per_frame": ms1,
-                                "note": "configs[1]: single clip; latency-bound small-M launches (split-K GEMMs)"}
+            ms1 = f0.elapsed_time(f1) / n1
+            model.infer_auto_regressive({"motion_input": m1_h, "audio_input": a1_h}, steps=8)   # untimed warm-up
+            stream.synchronize()
+            out1 = torch.empty(1, n1, dims.out_dim).pin_memory()
+            tb = time.perf_counter()
+            fr1 = model.infer_auto_regressive({"motion_input": m1_h, "audio_input": a1_h}, steps=n1)
+            out1.copy_(fr1, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            e2e1 = time.perf_counter() - tb
+            assert tuple(fr1.shape) == (1, n1, dims.out_dim) and torch.isfinite(out1).all()
+            extras["batch1"] = {"value": 1e3 / ms1, "unit": "frames/s", "ms_per_frame": ms1, "frames": n1,
+                                "audio_len": int(a1_h.shape[1]),
+                                "e2e": {"value": n1 / e2e1, "unit": "frames/s", "seconds_per_clip": e2e1,
+                                        "h2d_bytes": (m1_h.numel() + a1_h.numel()) * 4, "d2h_bytes": out1.numel() * 4},
+                                "note": "configs[1]: single clip, 1200 frames; latency-bound small-M launch chain"}
+            del h1, a1pad
           except Exception as exc:  # an extra must never cost the headline line
             extras["batch1"] = {"error": repr(exc)[:300]}
         if rank == 0 and not args.no_extras:
@@ -419,7 +626,9 @@ def run_ours(args):
             # per-frame launch counts of each GEMM at the cross-modal shape (encoder shapes are smaller)
             dom = max(("gemm_qkv", "gemm_out", "gemm_ff1", "gemm_ff2"), key=lambda k: kr[k]["s"])
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+            if not os.path.exists(tpath):
+                tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
             if args.mode == "precise" and B == 128 and os.path.exists(tpath):
                 with open(tpath) as f:
                     traffic = json.load(f).get(dom)
@@ -427,6 +636,8 @@ def run_ours(args):
                 "bound": "tensor", "kernel": f"gemm_tc2_kernel ({dom}, M={B * dims.cross_seq}, tcgen05 cta_group::2)",
                 "achieved": kr[dom]["executed_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": kr[dom]["executed_tflops"] / peaks["bf16_tflops"], "traffic": traffic,
+                "traffic_source": (os.path.relpath(tpath, ROOT) + " (ncu --set full dram__bytes_read+write per launch, "
+                                   "committed; not re-measured in this run)") if traffic is not None else None,
                 "frac_of_sustained_peak": kr[dom]["executed_tflops"] / peaks["bf16_tflops_sustained"],
                 "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                 "algorithmic_tflops": kr[dom]["algo_tflops"],
@@ -438,17 +649,42 @@ def run_ours(args):
                 "achieved": kr["attn_block"]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": kr["attn_block"]["frac_hbm"],
                 "sdpa_core_gbs": kr["sdpa"]["gbs"], "sdpa_core_frac": kr["sdpa"]["gbs"] / peaks["hbm_gbs"],
-                "note": "bytes = 1600*B*N*4 + weights (SURVEY.md 8d); the block is tensor-bound (289 GFLOP/launch)",
+                "bytes_per_element": kr["attn_block"]["s_el"],
+                "frac_at_2_bytes_per_element": kr["attn_block"]["frac_hbm_s2"],
+                "tensor_tflops_executed": kr["attn_block"]["executed_tflops"],
+                "tensor_frac": kr["attn_block"]["executed_tflops"] / peaks["bf16_tflops"],
+                "note": ("BASELINE's metric for the attention block: bytes = 1600*B*N*s + 2562400*s (SURVEY.md 8d: x in, y "
+                         "out, weights once), s = bytes_per_element (4 = fp32 residual stream / bf16 hi+lo operands; the "
+                         "survey's bf16 figure s = 2 is given beside it). The block executes 289 GFLOP algorithmic "
+                         "(x3 products in precise mode) per launch, i.e. it is tensor-bound by >9x: tensor_frac is the "
+                         "number that says how good the block is, the HBM fraction cannot approach 0.7 by construction"),
             }
           except Exception as exc:
             extras["roofline"] = {"error": repr(exc)[:300]}
+        sweep = None
+        if not args.no_extras and not args.no_sweep:
+            try:
+                sweep = run_sweep_leg(args, model, dev, world, rank, stream, barrier, max_over_ranks, peaks)
+            except Exception as exc:
+                if world > 1:
+                    raise                     # ranks must stay in lock step
+                sweep = {"error": repr(exc)[:300]}
     fps = world * B * K / (ms * 1e-3)
     e2e_fps = world * B * K / e2e_s
+    train = None
+    if not args.no_extras and not args.no_train:
+        try:
+            train = run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, max_over_ranks)
+        except Exception as exc:
+            if world > 1:
+                raise
+            train = {"error": repr(exc)[:300]}
 
     line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "warmup_requested": args.warmup,     # fewer than 3 requested warm-up steps are raised to 3
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (fp32-grade split products, fp32 accumulate)" if args.mode == "precise" else "bf16",
             "data": "synthetic",
@@ -463,6 +699,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
         }
         line.update(extras)
+        if sweep is not None:
+            line["batch_sweep"] = {"unit": "frames/s (all GPUs)", "n_gpus": world, "mode": args.mode, "points": sweep,
+                                   "note": "configs[4]: B clips per GPU, device-resident, 3 warm-up frames then "
+                                           "frames_timed frames on the captured graph; max over ranks"}
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_extras and not args.no_cpu:
             try:
                 cpu_fps, cpu_total, threads, desc = cpu_frames_per_sec(args.cpu_frames, 2, target_seconds=12.0)

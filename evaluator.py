@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--output_dir", default="outputs")
     ap.add_argument("--data_npz", default="")
     ap.add_argument("--tf_checkpoint", default="", help="TensorFlow checkpoint prefix (ckpt-N) to evaluate; default: "
-                    "the newest TF checkpoint in --model_dir if there is one, else the newest ckpt-*.pt")
+                    "whichever of the newest TF checkpoint and the newest ckpt-*.pt in --model_dir has the higher step")
     ap.add_argument("--num_clips", type=int, default=4)
     ap.add_argument("--steps", type=int, default=1200)
     ap.add_argument("--mode", default="precise", choices=["precise", "bf16"])
@@ -46,6 +46,14 @@ def main():
     tf_prefix = args.tf_checkpoint or tf_checkpoint.latest_checkpoint(args.model_dir)   # evaluator.py:56-60 restores TF
     ckpts = sorted(f for f in os.listdir(args.model_dir) if f.startswith("ckpt-") and f.endswith(".pt")) \
         if os.path.isdir(args.model_dir) else []
+    if tf_prefix and ckpts and not args.tf_checkpoint:
+        # both kinds present: the newer step wins (training may have continued without --export_tf_checkpoint)
+        import re
+        m = re.search(r"-(\d+)$", tf_prefix)
+        tf_step = int(m.group(1)) if m else -1
+        pt_step = int(ckpts[-1][len("ckpt-"):-len(".pt")])
+        if pt_step > tf_step:
+            tf_prefix = None
     if tf_prefix:
         model.set_weights(tf_checkpoint.load_fact_weights(tf_prefix, model.dims))
     elif ckpts:

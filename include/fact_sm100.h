@@ -8,6 +8,10 @@
  *  - every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer (no hidden allocation);
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 or a negative FACT_ERR_*;
  *    fact_last_error() returns a thread-local description of the last failure;
+ *  - threading: calls on distinct streams may run from distinct threads.  Process-wide state is limited to (a) the
+ *    fact_set_flag developer switches (plain ints: change them only while no call is in flight), (b) mutex-guarded
+ *    caches of TMA descriptors and of captured AR frame graphs (the latter owned by a fact_ar_session, see below), and
+ *    (c) per-thread, per-device helper streams / events;
  *  - activations are row-major fp32 [tokens, features]; "split" buffers are bf16 row-major, `hi` always present,
  *    `lo` present only in FACT_MODE_PRECISE (x ~= hi + lo, see DESIGN.md "bf16x3");
  *  - Keras weight layout is [in, out] row-major (y = x.W); packed GEMM weights are [out, in] bf16 (K-major);
@@ -36,7 +40,7 @@ extern "C" {
 #define FACT_MODE_BF16 1
 #define FACT_MODE_FP32_SIMT 2
 
-#define FACT_ABI_VERSION 2
+#define FACT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FACT_API __attribute__((visibility("default")))
@@ -238,11 +242,22 @@ FACT_API int fact_forward(const fact_dims* dims, const fact_weights* w, const fl
  * start_frame > 0 continues a previous one.  audio: [B, audio_len, audio_dim].
  * start_frame + n_frames must be <= min(hist_capacity, audio_len - audio_seq + 1) (the caller applies the early-stop
  * rule of fact_model.py:125-126).  step_counter: device int scratch.
- * use_graph != 0 replays one captured CUDA graph per frame (needs a non-default stream). */
+ * use_graph != 0 replays one captured CUDA graph per frame (needs a non-default stream).
+ * session: owner of the captured frame graphs (fact_ar_session_create), NULL = a process-wide default session.  A graph
+ * is keyed on everything it bakes in (the whole weight table, dims, buffers, sizes, mode, developer flags, device) and a
+ * session keeps at most 12 of them (least recently used evicted one at a time).  Destroy the session before freeing the
+ * weights / buffers its graphs point into -- e.g. together with the model object. */
 FACT_API int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist,
                                         int hist_capacity, const float* audio, int audio_len, int batch,
                                         int start_frame, int n_frames, int* step_counter, void* workspace,
-                                        size_t workspace_bytes, int mode, int use_graph, void* stream);
+                                        size_t workspace_bytes, int mode, int use_graph, void* session, void* stream);
+
+/* Owner of captured AR frame graphs.  create returns NULL on allocation failure; destroy(NULL) is a no-op; destroying a
+ * session whose graphs are still running is allowed (resources are released when the launches complete). */
+FACT_API void* fact_ar_session_create(void);
+FACT_API int fact_ar_session_destroy(void* session);
+/* Graphs currently cached by `session` (NULL = the default session): test / diagnostics seam. */
+FACT_API int fact_ar_session_graphs(void* session);
 
 /* ---- training blocks (bf16 product path; reference semantics: mint/ctl/single_task_trainer.py:138-199) -------- */
 
@@ -293,10 +308,20 @@ FACT_API size_t fact_train_workspace_bytes(const fact_dims* dims, int batch);
 /* One replica's train step up to the gradients (single_task_trainer.py:145-178): forward with saved activations,
  * *loss_out = FACTModel.loss(target, pred) (unscaled), gradients of loss * loss_scale ACCUMULATED into `g` (zero the
  * gradient buffers first; loss_scale = 1 / num_replicas as in :157-158).  bf16 products, fp32 everything else.
- * target: [B, target_len, out_dim]. */
+ * target: [B, target_len, out_dim].
+ * stage_events (optional, NULL = none): host array of two cudaEvent_t (either may be NULL).  [0] is recorded on `stream`
+ * once the gradients of the cross-modal stack and the output head are final, [1] once those of the motion encoder and
+ * its embeddings are too (the audio encoder's are final when the call's work completes).  They let a data-parallel host
+ * start the cross-replica sum of those slices of its gradient bucket on another stream while the rest of the backward
+ * runs (the bucket order of mint_b200/weights.py is cross stack + head, motion encoder, audio encoder). */
 FACT_API int fact_train_step(const fact_dims* dims, const fact_weights* w, const fact_grads* g, const float* motion,
                              const float* audio, const float* target, int target_len, int batch, float loss_scale,
-                             float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+                             float* loss_out, void* workspace, size_t workspace_bytes, void* const* stage_events,
+                             void* stream);
+
+/* g[i] *= clip_norm / max(sqrt(*sum_squares), clip_norm) -- tf.clip_by_global_norm (single_task_trainer.py:180-183)
+ * with the squared global norm read from DEVICE memory (fact_sum_squares output): no host synchronisation. */
+FACT_API int fact_clip_scale(float* g, long long n, const float* sum_squares, float clip_norm, void* stream);
 
 #ifdef __cplusplus
 }

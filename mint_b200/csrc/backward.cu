@@ -883,11 +883,37 @@ int cast_weight(const float* w, void* out, int rows, int cols, int ld_out, cudaS
   return FACT_OK;
 }
 
+// g *= clip / max(sqrt(*sumsq), clip): the factor of tf.clip_by_global_norm from a device-resident squared norm
+__global__ void clip_scale_kernel(float* __restrict__ g, long long n, const float* __restrict__ sumsq, float clip) {
+  const float norm = sqrtf(*sumsq);
+  const float f = clip / fmaxf(norm, clip);
+  if (f == 1.f) return;
+  const long long n4 = n / 4;
+  float4* g4 = reinterpret_cast<float4*>(g);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = g4[i];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    g4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - n4 * 4) g[n4 * 4 + threadIdx.x] *= f;
+}
+
 }  // namespace fact
 
 using namespace fact;
 
 // ------------------------------------------------------------------------------------------- C ABI (training blocks)
+extern "C" int fact_clip_scale(float* g, long long n, const float* sum_squares, float clip_norm, void* stream) {
+  FACT_REQUIRE(g && sum_squares && n > 0 && clip_norm > 0.f, FACT_ERR_BAD_SHAPE, "fact_clip_scale: bad arguments");
+  FACT_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, FACT_ERR_BAD_ALIGN, "fact_clip_scale: g must be 16-B aligned");
+  const long long blocks = (n / 4 + 255) / 256;
+  const int grid = static_cast<int>(blocks > 8192 ? 8192 : (blocks < 1 ? 1 : blocks));
+  clip_scale_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, sum_squares, clip_norm);
+  FACT_LAUNCH_CHECK("clip_scale_kernel");
+  return FACT_OK;
+}
+
 extern "C" int fact_wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dw, int ldw,
                                int tokens, int in_dim, int out_dim, void* stream) {
   return wgrad_gemm(x_bf16, ldx, dy_bf16, ldy, dw, ldw, tokens, in_dim, out_dim, as_stream(stream));

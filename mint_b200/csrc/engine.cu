@@ -8,9 +8,10 @@
 // (the tf.concat of base_models.py:192-193 costs nothing).  The AR loop keeps a device-side step counter: the
 // shift-by-one of fact_model.py:131 and the audio window slice of :124 are row offsets read by the embedding
 // kernel, so one captured CUDA graph is replayed once per generated frame.
+#include <string.h>
+
 #include <map>
 #include <mutex>
-#include <tuple>
 #include <vector>
 
 #include "fact_internal.h"
@@ -320,17 +321,28 @@ static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* mo
   // latency-bound launches, so the audio encoder runs on a second stream with its own scratch and joins before the
   // cross-modal stack (a fork / join inside the captured graph).  At large batch the GPU is full: one stream.
   const bool dual = g_dual_stream && ws.a_ln_hi != nullptr;
-  static thread_local cudaStream_t s2 = nullptr;
-  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t sa = st;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Workspace wa = ws;
   if (dual) {
-    if (!s2) {
-      FACT_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-      FACT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      FACT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    // side stream + fork / join events of the calling thread, one set per device (a stream or event of another device
+    // is an invalid resource handle on this one)
+    struct Side {
+      cudaStream_t s2 = nullptr;
+      cudaEvent_t fork = nullptr, join = nullptr;
+    };
+    static thread_local std::map<int, Side> sides;
+    int device = 0;
+    FACT_CUDA_CHECK(cudaGetDevice(&device));
+    Side& side = sides[device];
+    if (!side.s2) {
+      FACT_CUDA_CHECK(cudaStreamCreateWithFlags(&side.s2, cudaStreamNonBlocking));
+      FACT_CUDA_CHECK(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+      FACT_CUDA_CHECK(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
     }
-    sa = s2;
+    sa = side.s2;
+    ev_fork = side.fork;
+    ev_join = side.join;
     wa.ln_hi = ws.a_ln_hi; wa.ln_lo = ws.a_ln_lo; wa.ao_hi = ws.a_ao_hi; wa.ao_lo = ws.a_ao_lo;
     wa.qkv_hi = ws.a_qkv_hi; wa.qkv_lo = ws.a_qkv_lo; wa.h_hi = ws.a_h_hi; wa.h_lo = ws.a_h_lo;
     wa.splitk = ws.a_splitk; wa.splitk_bytes = ws.a_splitk_bytes;
@@ -378,18 +390,46 @@ static int check_weights(const fact_dims* dm, const fact_weights* w) {
 
 // ---- graph cache for the AR loop
 int g_ar_prune = 1;  // fact_set_flag("ar_prune", 0): run the full last layer (A-B check of the row-0 pruning)
+int g_ar_fused = 1;  // reserved for the fused small-batch decode path (fact_set_flag("ar_fused", 0) disables it)
 extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn, g_gemm_finish_ln;
 
+// One captured frame is valid for exactly the pointers and sizes it was captured with, so the key is EVERYTHING the
+// capture bakes in: the whole weight table (every pointer of every layer), the dims, every developer flag, the call's
+// buffers and sizes.
 struct GraphKey {
   std::vector<uintptr_t> v;
-  bool operator<(const GraphKey& o) const { return v < o.v; }
+  bool operator==(const GraphKey& o) const { return v == o.v; }
+  void add(uintptr_t x) { v.push_back(x); }
+  void add_bytes(const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i += sizeof(uintptr_t)) {
+      uintptr_t w = 0;
+      memcpy(&w, b + i, n - i < sizeof(uintptr_t) ? n - i : sizeof(uintptr_t));
+      v.push_back(w);
+    }
+  }
 };
-static std::mutex g_graph_mu;
-struct CachedGraph {
-  cudaGraphExec_t exec;
-  long long kernels;  // kernel nodes of one frame
+
+// Graph executables belong to a session (fact_ar_session_create): a model owns one and destroys it with itself, so a
+// stale graph cannot outlive the buffers it points into.  Calls without a session share a process-wide default one.
+// Bounded, least-recently-used eviction of ONE entry at a time; destroying an executable that is still running on a
+// stream is legal (its resources are released when the launch completes).
+struct ArSession {
+  struct Entry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    long long kernels;  // kernel nodes of one frame
+    unsigned long long last_use;
+  };
+  std::mutex mu;
+  std::vector<Entry> entries;
+  unsigned long long tick = 0;
+  static constexpr size_t kCapacity = 12;
+  ~ArSession() {
+    for (auto& e : entries) cudaGraphExecDestroy(e.exec);
+  }
 };
-static std::map<GraphKey, CachedGraph> g_graphs;
+static ArSession g_default_session;
 
 }  // namespace fact
 
@@ -434,10 +474,24 @@ extern "C" int fact_forward(const fact_dims* dims, const fact_weights* w, const 
                    dims->out_dim, d, &e, st);
 }
 
+extern "C" void* fact_ar_session_create(void) { return new (std::nothrow) ArSession(); }
+
+extern "C" int fact_ar_session_destroy(void* session) {
+  delete static_cast<ArSession*>(session);
+  return FACT_OK;
+}
+
+extern "C" int fact_ar_session_graphs(void* session) {
+  ArSession* s = session ? static_cast<ArSession*>(session) : &g_default_session;
+  std::lock_guard<std::mutex> lk(s->mu);
+  return static_cast<int>(s->entries.size());
+}
+
 extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weights* w, float* motion_hist,
                                           int hist_capacity, const float* audio, int audio_len, int batch,
                                           int start_frame, int n_frames, int* step_counter, void* workspace,
-                                          size_t workspace_bytes, int mode, int use_graph, void* stream) {
+                                          size_t workspace_bytes, int mode, int use_graph, void* session,
+                                          void* stream) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_weights(dims, w))) return rc;
@@ -488,23 +542,38 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
   FACT_REQUIRE(st != nullptr, FACT_ERR_UNSUPPORTED,
                "graph replay needs a non-default stream (capture is illegal on the legacy stream)");
   GraphKey key;
-  key.v = {reinterpret_cast<uintptr_t>(w->cross_layers[0].wqkv_hi), reinterpret_cast<uintptr_t>(w->out_w),
-           reinterpret_cast<uintptr_t>(motion_hist), reinterpret_cast<uintptr_t>(audio),
-           reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
-           static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch), static_cast<uintptr_t>(hist_capacity),
-           static_cast<uintptr_t>(mode), static_cast<uintptr_t>(dims->cross_layers + 1000 * g_ar_prune + 10000 * g_gemm_pair + 100000 * g_gemm_splitk +
-                                  1000000 * g_sdpa_legacy + 10000000 * g_dual_stream + 100000000 * g_gemm_tma_store +
-                                  1000000000ull * g_gemm_finish_ln),
-           static_cast<uintptr_t>(dims->d_model)};
+  key.add_bytes(dims, sizeof(*dims));
+  key.add_bytes(w->motion_layers, sizeof(fact_layer_weights) * dims->motion_layers);
+  key.add_bytes(w->audio_layers, sizeof(fact_layer_weights) * dims->audio_layers);
+  key.add_bytes(w->cross_layers, sizeof(fact_layer_weights) * dims->cross_layers);
+  {
+    fact_weights flat = *w;  // the three host-array pointers are not device state: their contents were added above
+    flat.motion_layers = flat.audio_layers = flat.cross_layers = nullptr;
+    key.add_bytes(&flat, sizeof(flat));
+  }
+  for (uintptr_t x : {reinterpret_cast<uintptr_t>(motion_hist), reinterpret_cast<uintptr_t>(audio),
+                      reinterpret_cast<uintptr_t>(step_counter), reinterpret_cast<uintptr_t>(workspace),
+                      static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch),
+                      static_cast<uintptr_t>(hist_capacity), static_cast<uintptr_t>(mode)})
+    key.add(x);
+  for (int f : {g_ar_prune, g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_dual_stream, g_gemm_tma_store, g_gemm_bn,
+                g_gemm_finish_ln, g_ar_fused})
+    key.add(static_cast<uintptr_t>(f));
+  int device = 0;
+  FACT_CUDA_CHECK(cudaGetDevice(&device));
+  key.add(static_cast<uintptr_t>(device));
+  ArSession* sess = session ? static_cast<ArSession*>(session) : &g_default_session;
   cudaGraphExec_t exec = nullptr;
   long long frame_kernels = 0;
   {
-    std::lock_guard<std::mutex> lk(g_graph_mu);
-    auto it = g_graphs.find(key);
-    if (it != g_graphs.end()) {
-      exec = it->second.exec;
-      frame_kernels = it->second.kernels;
-    }
+    std::lock_guard<std::mutex> lk(sess->mu);
+    for (auto& e : sess->entries)
+      if (e.key == key) {
+        exec = e.exec;
+        frame_kernels = e.kernels;
+        e.last_use = ++sess->tick;
+        break;
+      }
   }
   if (!exec) {
     cudaGraph_t graph = nullptr;
@@ -522,12 +591,15 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
     ce = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
-    std::lock_guard<std::mutex> lk(g_graph_mu);
-    if (g_graphs.size() >= 16) {  // bounded: drop everything (idle graphs only; callers sync between shapes)
-      for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
-      g_graphs.clear();
+    std::lock_guard<std::mutex> lk(sess->mu);
+    if (sess->entries.size() >= ArSession::kCapacity) {  // evict the least recently used entry only
+      size_t victim = 0;
+      for (size_t i = 1; i < sess->entries.size(); ++i)
+        if (sess->entries[i].last_use < sess->entries[victim].last_use) victim = i;
+      cudaGraphExecDestroy(sess->entries[victim].exec);
+      sess->entries.erase(sess->entries.begin() + victim);
     }
-    g_graphs[key] = CachedGraph{exec, frame_kernels};
+    sess->entries.push_back(ArSession::Entry{key, exec, frame_kernels, ++sess->tick});
   }
   for (int i = 0; i < n_frames; ++i) FACT_CUDA_CHECK(cudaGraphLaunch(exec, st));
   g_launch_count += frame_kernels * n_frames;

@@ -259,7 +259,8 @@ extern "C" size_t fact_train_workspace_bytes(const fact_dims* dims, int batch) {
 
 extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, const fact_grads* g, const float* motion,
                                const float* audio, const float* target, int target_len, int batch, float loss_scale,
-                               float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+                               float* loss_out, void* workspace, size_t workspace_bytes,
+                               void* const* stage_events, void* stream) {
   FACT_REQUIRE(dims && w && g && motion && audio && target && loss_out && batch > 0, FACT_ERR_BAD_SHAPE,
                "fact_train_step: bad arguments");
   const int d = dims->d_model, ns = dims->motion_seq + dims->audio_seq, od = dims->out_dim, odp = head_pad(od);
@@ -333,6 +334,8 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
     if ((rc = layer_bwd(dims, w->cross_layers[l], g->cross_layers[l], Sc[l], batch, ns, ws.dy, ws,
                         l + 1 < dims->cross_layers, l > 0 ? g->cross_layers[l - 1].b2 : nullptr, st)))
       return rc;
+  // gradients of the cross-modal stack and the head are final: the host may start reducing that part of the bucket
+  if (stage_events && stage_events[0]) FACT_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(stage_events[0]), st));
   // tf.concat backward (base_models.py:192-193): rows [0, motion_seq) -> motion encoder, the rest -> audio encoder
   if ((rc = slice_rows(ws.dy, ws.dym, static_cast<long long>(batch) * dims->motion_seq, d, dims->motion_seq, ns, 0, st)))
     return rc;
@@ -347,6 +350,7 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   if ((rc = embed_bwd_train(ws.em_x, ws.em_kp, ws.dym, ws.dy_b, g->motion_embed_w, g->motion_pos, batch,
                             dims->motion_seq, dims->motion_dim, d, st)))
     return rc;
+  if (stage_events && stage_events[1]) FACT_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(stage_events[1]), st));
   for (int l = dims->audio_layers - 1; l >= 0; --l)
     if ((rc = layer_bwd(dims, w->audio_layers[l], g->audio_layers[l], Sa[l], batch, dims->audio_seq, ws.dya, ws,
                         l + 1 < dims->audio_layers, l > 0 ? g->audio_layers[l - 1].b2 : g->audio_embed_b, st)))

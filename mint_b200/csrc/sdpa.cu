@@ -274,53 +274,31 @@ extern int g_gemm_finish_ln;
 extern int g_sdpa_bwd_tc;
 extern int g_dual_stream;
 extern int g_ar_prune;
+extern int g_ar_fused;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
 
 }  // namespace fact
 
 using namespace fact;
 
+// Developer switches: process-global on purpose (A/B timing of kernel variants, tests).  Plain ints written here and
+// read at dispatch time: set them while no other thread is inside the library.  Every one is part of the AR graph key.
 extern "C" int fact_set_flag(const char* name, int value) {
-  if (name && strcmp(name, "sdpa_legacy") == 0) {
-    g_sdpa_legacy = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "ar_prune") == 0) {
-    g_ar_prune = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "dual_stream") == 0) {
-    g_dual_stream = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "gemm_bn") == 0) {
-    g_gemm_bn = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "sdpa_bwd_tc") == 0) {
-    g_sdpa_bwd_tc = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "gemm_finish_ln") == 0) {
-    g_gemm_finish_ln = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "wgrad_pair") == 0) {
-    g_wgrad_pair = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "gemm_tma_store") == 0) {
-    g_gemm_tma_store = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "gemm_splitk") == 0) {
-    g_gemm_splitk = value;
-    return FACT_OK;
-  }
-  if (name && strcmp(name, "gemm_pair") == 0) {
-    g_gemm_pair = value;
-    return FACT_OK;
-  }
+  struct Flag {
+    const char* name;
+    int* slot;
+  };
+  const Flag flags[] = {{"sdpa_legacy", &g_sdpa_legacy},   {"ar_prune", &g_ar_prune},
+                        {"dual_stream", &g_dual_stream},   {"gemm_bn", &g_gemm_bn},
+                        {"sdpa_bwd_tc", &g_sdpa_bwd_tc},   {"gemm_finish_ln", &g_gemm_finish_ln},
+                        {"wgrad_pair", &g_wgrad_pair},     {"gemm_tma_store", &g_gemm_tma_store},
+                        {"gemm_splitk", &g_gemm_splitk},   {"gemm_pair", &g_gemm_pair},
+                        {"ar_fused", &g_ar_fused}};
+  for (const Flag& f : flags)
+    if (name && strcmp(name, f.name) == 0) {
+      *f.slot = value;
+      return FACT_OK;
+    }
   set_error("fact_set_flag: unknown flag %s", name ? name : "(null)");
   return FACT_ERR_UNSUPPORTED;
 }

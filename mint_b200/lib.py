@@ -50,7 +50,7 @@ class Grads(C.Structure):
         "out_w", "out_b")]
 
 
-ABI_VERSION = 2  # FACT_ABI_VERSION of include/fact_sm100.h these ctypes declarations mirror
+ABI_VERSION = 3  # FACT_ABI_VERSION of include/fact_sm100.h these ctypes declarations mirror
 
 
 class GemmEpilogue(C.Structure):

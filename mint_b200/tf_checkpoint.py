@@ -17,9 +17,23 @@ Pinning: the table / entry / tensor layer is checked against a REAL TensorFlow-w
 reference tree (third_party/tf_models/research/lfads/synth_data/trained_itb/model-65000.*: every block and tensor
 checksum verifies and the writer reproduces its `.index` and `.data` files byte for byte -- the committed golden is
 the decoded tensors plus TensorFlow's file hashes, tests/golden/make_tf_bundle_golden.py).  That file is a
-TF1 Saver bundle without an object graph, so the object-graph message numbers and the string-tensor framing below
-follow the published TensorFlow sources from memory and are exercised only by this module's own writer:
-**object-graph layer unpinned**.
+TF1 Saver bundle without an object graph.  The object-graph MESSAGE layer is pinned to TensorFlow's own generated
+protobuf module for tensorflow/core/protobuf/trackable_object_graph.proto, which ships in this image inside
+tensorboard (`tensorboard.compat.proto.trackable_object_graph_pb2`): tests/test_tf_checkpoint.py parses the bytes this
+module writes with that class, and feeds this module's reader graphs serialised by it (slot variables, registered
+savers, children in any order, fields this reader does not know).  Field numbers, from that descriptor:
+    TrackableObjectGraph.nodes = 1 (repeated TrackableObject)
+    TrackableObject: children = 1 (ObjectReference), attributes = 2 (SerializedTensor), slot_variables = 3,
+                     registered_saver = 4, has_checkpoint_values = 5
+    ObjectReference: node_id = 1 (int32), local_name = 2
+    SerializedTensor: name = 1, full_name = 2, checkpoint_key = 3
+    SlotVariableReference: original_variable_node_id = 1, slot_name = 2, slot_variable_node_id = 3
+DataType numbers: tensorflow/core/framework/types.proto (same check against tensorboard.compat.proto.types_pb2).
+What remains from the published TensorFlow sources only (tensor_bundle.cc WriteStringTensor) is the string-tensor
+framing that carries the graph: varint64 lengths | masked crc32c of the lengths taken as uint32 each (uint64 only
+above 4 GiB) | bytes, entry checksum = masked running crc over lengths, length checksum and bytes.  No
+TensorFlow-written TF2 checkpoint exists in the reference tree or the image: **loading the released FACT checkpoint
+is untested**; INTEGRATION.md says so.
 """
 from __future__ import annotations
 
@@ -244,6 +258,11 @@ def _entry_bytes(e: Entry) -> bytes:
     return out
 
 
+def _length_word(n: int) -> bytes:
+    """How WriteStringTensor feeds a string length to the checksum."""
+    return struct.pack("<I", n) if n <= 0xFFFFFFFF else struct.pack("<Q", n)
+
+
 class Bundle:
     """Reader for `<prefix>.index` + `<prefix>.data-XXXXX-of-YYYYY`."""
 
@@ -289,17 +308,26 @@ class Bundle:
         return arr.reshape(e.shape).copy()
 
     @staticmethod
-    def _strings(e: Entry, data: bytes):
+    def _strings(e: Entry, data: bytes, verify: bool = True):
+        """tensor_bundle.cc ReadStringTensor: lengths, their checksum, bytes; both checksums verified."""
         n = int(np.prod(e.shape)) if e.shape else 1
         lens, pos = [], 0
         for _ in range(n):
             v, pos = _varint(data, pos)
             lens.append(v)
-        pos += 4                                         # masked crc32c of the lengths
+        len_bytes = b"".join(_length_word(v) for v in lens)
+        stored = data[pos:pos + 4]
+        if verify and (len(stored) != 4 or struct.unpack("<I", stored)[0] != masked_crc(len_bytes)):
+            raise ValueError("string tensor: length checksum mismatch")
+        pos += 4
         out = []
         for ln in lens:
+            if pos + ln > len(data):
+                raise ValueError("string tensor: truncated")
             out.append(data[pos:pos + ln])
             pos += ln
+        if verify and not _mask_ok(e.crc, len_bytes + stored + b"".join(out)):
+            raise ValueError("string tensor: checksum mismatch")
         return np.array(out, dtype=object).reshape(e.shape)
 
     # ---- TF2 object graph
@@ -356,14 +384,14 @@ class BundleWriter:
         self._data += data
 
     def add_string_scalar(self, key: str, value: bytes) -> None:
+        """tensor_bundle.cc WriteStringTensor for a scalar: the running crc takes each length as a uint32 (a uint64
+        only above UINT32_MAX), then the 4 bytes of the masked length checksum, then the string bytes."""
         lens = _put_varint(len(value))
-        c = crc32c(struct.pack("<Q", len(value)))
-        len_ck = struct.pack("<I", (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF)
+        word = _length_word(len(value))
+        len_ck = struct.pack("<I", masked_crc(word))
         data = lens + len_ck + value
-        # entry checksum: running crc over the 8-byte lengths, the 4-byte length checksum and the string bytes
-        total = crc32c(struct.pack("<Q", len(value)) + len_ck + value)
-        masked = (((total >> 15) | (total << 17)) + 0xA282EAD8) & 0xFFFFFFFF
-        self._items[key.encode()] = _entry_bytes(Entry(DT_STRING, (), 0, len(self._data), len(data), masked))
+        self._items[key.encode()] = _entry_bytes(Entry(DT_STRING, (), 0, len(self._data), len(data),
+                                                       masked_crc(word + len_ck + value)))
         self._data += data
 
     def add_object_graph(self, path_to_key: dict) -> None:

@@ -2,12 +2,17 @@
 
 Same step semantics: pop the label, forward, `loss / num_replicas`, gradients, optional per-replica
 clip_by_global_norm BEFORE the cross-replica sum (single_task_trainer.py:180-183), one SUM all-reduce of all gradients
-(what MirroredStrategy does inside apply_gradients, :186-187), Adam.  One process per GPU; the all-reduce is a single
-NCCL call on the model's flat gradient bucket.
+(what MirroredStrategy does inside apply_gradients, :186-187), Adam.  One process per GPU.
+
+The cross-replica sum is ONE logical all-reduce of the model's flat gradient bucket, issued in the three contiguous
+slices the backward pass finishes in turn (FACTModel.gradient_stages: cross-modal stack + head, motion encoder, audio
+encoder).  The first two run on a side stream behind the events fact_train_step records, so they overlap the rest of
+the backward; only the last (smallest) slice is exposed.  Clipping needs the norm of the whole gradient before any
+slice may be summed, so with grad_clip_norm > 0 the reduce is a single call after the backward; the clip factor is
+computed and applied on the device (no host synchronisation).
 """
 from __future__ import annotations
 
-import math
 import time
 
 import torch
@@ -16,8 +21,10 @@ import torch.distributed as dist
 
 class SingleTaskTrainer:
     def __init__(self, train_dataset, label_key, model, loss_fn=None, optimizer=None, metrics=None,
-                 trainer_options=None, summary_fn=None, grad_clip_norm: float = 0.0):
-        """train_dataset: iterable of dict batches (torch / numpy); label_key: 'target' (trainer.py:157)."""
+                 trainer_options=None, summary_fn=None, grad_clip_norm: float = 0.0, overlap_allreduce: bool = True,
+                 allreduce: bool = True):
+        """train_dataset: iterable of dict batches (torch / numpy); label_key: 'target' (trainer.py:157).
+        allreduce=False skips the cross-replica sum (bench.py uses it to measure how much of it is exposed)."""
         self.train_dataset = train_dataset
         self.label_key = label_key
         self.model = model
@@ -28,6 +35,17 @@ class SingleTaskTrainer:
         self._steps = 0
         self._iter = None
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.allreduce = allreduce
+        self.overlap = bool(overlap_allreduce) and hasattr(model, "gradient_stages")
+        self._comm = None
+        self._events = None
+        self._sumsq = None
+        dev = getattr(model, "device", torch.device("cpu"))
+        if self.world > 1 and self.overlap and dev.type == "cuda":
+            self._comm = torch.cuda.Stream(dev)
+            self._events = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._events:
+                e.record(torch.cuda.current_stream(dev))     # creates the cudaEvent_t the C ABI re-records
 
     def train_loop_begin(self):
         self.train_loss, self._steps = 0.0, 0
@@ -36,14 +54,30 @@ class SingleTaskTrainer:
     def train_step(self, inputs: dict) -> torch.Tensor:
         inputs = dict(inputs)
         target = inputs.pop(self.label_key)                                     # :145
-        loss = self.model.forward_backward(inputs, target, loss_scale=1.0 / self.world)   # :151-158, 178
-        grad_scale = 1.0
-        if self.grad_clip_norm > 0:                                             # :180-183, per replica, before the sum
-            grad_scale = clip_scale(self.model, self.grad_clip_norm)
-            if grad_scale != 1.0:
-                self.model.flat_gradients.mul_(grad_scale)
-        if self.world > 1:                                                      # :186-187 (cross-replica SUM)
-            dist.all_reduce(self.model.flat_gradients, op=dist.ReduceOp.SUM)
+        clip = self.grad_clip_norm > 0
+        reduce = self.world > 1 and self.allreduce
+        staged = reduce and self.overlap and not clip
+        kw = {"stage_events": self._events} if staged and self._events else {}
+        loss = self.model.forward_backward(inputs, target, loss_scale=1.0 / self.world, **kw)   # :151-158, 178
+        grads = self.model.flat_gradients
+        if clip:                                                                # :180-183, per replica, before the sum
+            clip_by_global_norm_(self.model, self.grad_clip_norm, self)
+        if staged:                                                              # :186-187 (cross-replica SUM)
+            stages = self.model.gradient_stages()
+            if self._comm is not None:
+                cur = torch.cuda.current_stream(grads.device)
+                with torch.cuda.stream(self._comm):
+                    for (off, cnt), ev in zip(stages[:2], self._events):
+                        self._comm.wait_event(ev)
+                        dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)
+                off, cnt = stages[2]
+                dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)     # behind the whole backward
+                cur.wait_stream(self._comm)
+            else:
+                for off, cnt in stages:
+                    dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)
+        elif reduce:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
         self.optimizer.apply_gradients()
         self.model.global_step = self.optimizer.iterations
         return loss
@@ -61,21 +95,49 @@ class SingleTaskTrainer:
         return self.train_loop_end(total)
 
     def train_loop_end(self, total_loss=None):
-        """Same scalar names as single_task_trainer.py:201-211."""
+        """Same scalar names as single_task_trainer.py:201-211.  The reference feeds `loss / num_replicas` to a Keras
+        Mean metric on every replica (:157-158, :189-190); under MirroredStrategy its total and count are summed over
+        replicas on read, so the logged value is the mean over replicas AND steps of the SCALED loss (= mean loss /
+        num_replicas).  Reproduced literally: one all-reduce per logging loop, not per step."""
         n = max(self._steps, 1)
+        if total_loss is not None and self.world > 1 and torch.is_tensor(total_loss):
+            total_loss = total_loss.detach().clone() / self.world
+            dist.all_reduce(total_loss, op=dist.ReduceOp.SUM)
+            total_loss = total_loss / self.world
         mean = float(total_loss) / n if total_loss is not None else float("nan")
         dt = time.perf_counter() - self._t0
         return {"training_loss": mean, "task_loss": mean, "regularization_loss": 0.0,
                 "learning_rate": self.optimizer.current_lr(), "steps_per_second": n / dt if dt > 0 else float("nan")}
 
 
+def clip_by_global_norm_(model, clip_norm: float, owner=None) -> None:
+    """tf.clip_by_global_norm in place on the flat gradient bucket: g *= clip_norm / max(||g||, clip_norm).  The squared
+    norm stays in device memory (fact_sum_squares -> fact_clip_scale): no host round trip in the step."""
+    g = model.flat_gradients
+    if g.device.type != "cuda":                      # host-logic tests (gloo): same arithmetic in torch
+        norm = g.double().pow(2).sum().sqrt()
+        g.mul_(float(clip_norm) / max(float(norm), float(clip_norm)))
+        return
+    from . import lib
+    buf = getattr(owner, "_sumsq", None)
+    if buf is None:
+        buf = torch.zeros((), dtype=torch.float32, device=g.device)
+        if owner is not None:
+            owner._sumsq = buf
+    with torch.cuda.device(g.device):
+        st = torch.cuda.current_stream(g.device).cuda_stream
+        lib.check(lib.load().fact_sum_squares(g.data_ptr(), g.numel(), buf.data_ptr(), st), "fact_sum_squares")
+        lib.check(lib.load().fact_clip_scale(g.data_ptr(), g.numel(), buf.data_ptr(), float(clip_norm), st),
+                  "fact_clip_scale")
+
+
 def clip_scale(model, clip_norm: float) -> float:
-    """tf.clip_by_global_norm factor: clip_norm / max(global_norm, clip_norm)."""
+    """The clip factor as a host float (diagnostics / tests; synchronises)."""
     from . import lib
     g = model.flat_gradients
     out = torch.zeros((), dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device):
         lib.check(lib.load().fact_sum_squares(g.data_ptr(), g.numel(), out.data_ptr(),
                                               torch.cuda.current_stream(g.device).cuda_stream), "fact_sum_squares")
-    norm = math.sqrt(float(out))
+    norm = float(out) ** 0.5
     return clip_norm / max(norm, clip_norm)

@@ -1,4 +1,5 @@
 """TFRecord / tf.train.Example reader-writer and the reference's fact_preprocessing windowing (no TensorFlow)."""
+import os
 import struct
 
 import numpy as np
@@ -128,3 +129,67 @@ def test_fact_preprocessing_matches_the_references_own_code():
     np.testing.assert_array_equal(ev["motion_input"], g["eval_motion_input"])
     np.testing.assert_array_equal(ev["audio_input"], g["eval_audio_input"])
     assert "target" not in ev
+
+
+# ---------------------------------------------------------------------------- pinned to TensorFlow-written record files
+def _tfrecord_manifest():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tfrecord_manifest.json")) as f:
+        return json.load(f)
+
+
+def test_masked_crc_matches_every_length_checksum_tensorflow_wrote():
+    """14 TF-written known answers: masked crc32c of the 8-byte little-endian record length."""
+    import struct
+    man = _tfrecord_manifest()
+    n = 0
+    for info in man["files"].values():
+        for rec in info["records"]:
+            assert inputs.masked_crc(struct.pack("<Q", rec["length"])) == rec["length_masked_crc32c"]
+            n += 1
+    assert n == 14
+
+
+def test_reader_and_writer_on_a_record_tensorflow_wrote(tmp_path):
+    """tests/golden/tf_written_record.bin is one framed record copied bit for bit out of a TensorFlow-written file
+    (tests/golden/make_tfrecord_golden.py): the reader verifies both checksums, the Example parser reproduces the
+    manifest's feature table, and the writer re-frames the payload into the identical bytes."""
+    import hashlib
+    from tests.golden.make_tfrecord_golden import feature_summary
+    man = _tfrecord_manifest()
+    fx = man["fixture"]
+    path = os.path.join(os.path.dirname(__file__), "golden", fx["path"])
+    raw = open(path, "rb").read()
+    assert hashlib.sha256(raw).hexdigest() == fx["sha256"]
+    recs = list(inputs.read_tfrecords(path, verify_payload_crc=True))
+    assert len(recs) == 1
+    want = man["files"][fx["file"]]["records"][fx["record"]]
+    assert len(recs[0]) == want["length"] and hashlib.sha256(recs[0]).hexdigest() == want["payload_sha256"]
+    assert inputs.masked_crc(recs[0]) == want["payload_masked_crc32c"]
+    got = {k: list(v) for k, v in feature_summary(recs[0]).items()}
+    assert got == {k: list(v) for k, v in want["features"].items()}
+    out = tmp_path / "again.record"
+    with inputs.TFRecordWriter(str(out)) as w:
+        w.write(recs[0])
+    assert out.read_bytes() == raw
+    # a flipped payload bit must be caught
+    bad = bytearray(raw)
+    bad[40] ^= 1
+    (tmp_path / "bad.record").write_bytes(bytes(bad))
+    with pytest.raises(IOError):
+        list(inputs.read_tfrecords(str(tmp_path / "bad.record"), verify_payload_crc=True))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/third_party/tf_models"),
+                    reason="the TensorFlow-written record files live in the reference tree (build container only)")
+def test_every_tensorflow_written_record_file_in_the_reference_tree():
+    import hashlib
+    from tests.golden.make_tfrecord_golden import BASE, feature_summary
+    man = _tfrecord_manifest()
+    for rel, info in man["files"].items():
+        recs = list(inputs.read_tfrecords(BASE + rel, verify_payload_crc=True))
+        assert len(recs) == len(info["records"])
+        for payload, want in zip(recs, info["records"]):
+            assert hashlib.sha256(payload).hexdigest() == want["payload_sha256"]
+            assert {k: list(v) for k, v in feature_summary(payload).items()} == \
+                   {k: list(v) for k, v in want["features"].items()}

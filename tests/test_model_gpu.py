@@ -252,3 +252,39 @@ def test_cuda_path_matches_reference_code_at_fact_v5_size(cuda, fact_lib):
     err_ar = O.per_joint_l2(ar, g["ar"])
     print("vs reference code, fact_v5: call", err, "AR", err_ar)
     assert ar.shape == (1, 2, 225) and err <= PARITY_TOL and err_ar <= PARITY_TOL
+
+
+def test_ar_graphs_belong_to_the_model_session(cuda, fact_lib):
+    """Captured frame graphs are owned by the model's session: repeated calls of one shape reuse ONE graph (the staging
+    buffers make the key stable by construction), a second model has its own session, the default session stays empty,
+    and a model that is freed takes its graphs with it."""
+    dims = oracle_dims(audio_dim=35, **SMALL)
+    w = O.init_weights(dims, seed=3)
+    inp = O.synthetic_inputs(dims, batch=2, audio_len=dims.audio_seq + 5, seed=3)
+    tin = {k: torch.from_numpy(v).float() for k, v in inp.items() if k != "target"}
+    a = _model(make_config(**SMALL), w, "precise")
+    base_default = fact_lib.fact_ar_session_graphs(None)
+    first = a.infer_auto_regressive(tin, steps=6)
+    assert fact_lib.fact_ar_session_graphs(a._session) == 1
+    for _ in range(3):
+        again = a.infer_auto_regressive(tin, steps=6)
+        assert torch.equal(again, first)
+    assert fact_lib.fact_ar_session_graphs(a._session) == 1            # same staging buffers -> same key
+    a.infer_auto_regressive(tin, steps=3)                               # another shape: a second graph
+    assert fact_lib.fact_ar_session_graphs(a._session) == 2
+    b = _model(make_config(**SMALL), O.init_weights(dims, seed=4), "precise")
+    other = b.infer_auto_regressive(tin, steps=6)
+    assert fact_lib.fact_ar_session_graphs(b._session) == 1 and not torch.equal(other, first)
+    assert fact_lib.fact_ar_session_graphs(None) == base_default        # nothing leaked into the default session
+    # new weights in the same model: set_weights repacks in place (same pointers, new values) -> the graph still valid
+    a.set_weights(O.init_weights(dims, seed=4))
+    assert torch.equal(a.infer_auto_regressive(tin, steps=6), other)
+    # a session keeps at most 12 graphs, evicting one at a time
+    for steps in range(1, 6):
+        for extra in range(3):
+            t2 = dict(tin)
+            t2["audio_input"] = torch.cat([tin["audio_input"], tin["audio_input"][:, :extra + 1]], dim=1)
+            a.infer_auto_regressive(t2, steps=steps)
+    assert fact_lib.fact_ar_session_graphs(a._session) <= 12
+    assert torch.equal(a.infer_auto_regressive(tin, steps=6), other)
+    del a, b

@@ -5,6 +5,7 @@ import hashlib
 import json
 import os
 import shutil
+import struct
 
 import numpy as np
 import pytest
@@ -15,6 +16,10 @@ from tests.helpers import make_config
 
 def _dims(**kw):
     return config_util.resolve_fact_dims(make_config(**kw))
+
+
+def _small_dims():
+    return _dims(d=64, heads=4, ff=128, layers=(1, 2, 3), motion_seq=12, audio_seq=20)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MANIFEST = json.load(open(os.path.join(GOLD, "tf_bundle_manifest.json")))
@@ -148,3 +153,175 @@ def test_latest_checkpoint_follows_the_state_file_then_the_numbers(tmp_path):
     assert T.latest_checkpoint(d) == os.path.join(d, "ckpt-2000")          # the state file wins, as in TF
     os.remove(os.path.join(d, "ckpt-2000.index"))
     assert T.latest_checkpoint(d) == os.path.join(d, "ckpt-3000")          # stale state file: fall back
+
+
+# ------------------------------------------------------- object-graph layer vs TensorFlow's own generated proto module
+def _tf_graph_pb2():
+    """tensorflow/core/protobuf/trackable_object_graph.proto as generated by TensorFlow's build, shipped in tensorboard."""
+    return pytest.importorskip("tensorboard.compat.proto.trackable_object_graph_pb2")
+
+
+def test_dtype_numbers_match_tensorflows_types_proto():
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    for name in ("DT_FLOAT", "DT_DOUBLE", "DT_INT32", "DT_STRING", "DT_INT64", "DT_BOOL", "DT_BFLOAT16", "DT_HALF"):
+        assert getattr(T, name) == getattr(types_pb2, name), name
+
+
+def test_written_object_graph_parses_with_tensorflows_proto_class(tmp_path):
+    pb = _tf_graph_pb2()
+    dims = _small_dims()
+    w = {n: np.random.default_rng(0).standard_normal(s).astype(np.float32) for n, s in W.variable_shapes(dims).items()}
+    prefix = str(tmp_path / "ckpt-7")
+    T.save_fact_weights(prefix, w, dims, step=7)
+    b = T.Bundle(prefix)
+    raw = b.tensor(T.OBJECT_GRAPH_KEY).reshape(-1)[0]          # both string checksums verified on the way
+    g = pb.TrackableObjectGraph.FromString(raw)
+    # walk it with TensorFlow's message classes exactly as the checkpoint loader would: by local_name from the root
+    paths = T.fact_object_paths(dims)
+    for name, path in list(paths.items()) + [("iter", "optimizer/iter")]:
+        node = g.nodes[0]
+        for part in path.split("/"):
+            nxt = [c for c in node.children if c.local_name == part]
+            assert len(nxt) == 1, (path, part)
+            node = g.nodes[nxt[0].node_id]
+        attr = [a for a in node.attributes if a.name == "VARIABLE_VALUE"]
+        assert len(attr) == 1 and attr[0].checkpoint_key == path + T.VAR_SUFFIX
+        assert attr[0].full_name == path
+        if name != "iter":
+            np.testing.assert_array_equal(b.tensor(attr[0].checkpoint_key), w[name])
+    # and the bytes are canonical: TensorFlow's class re-serialises them identically
+    assert g.SerializeToString() == raw
+
+
+def test_reader_on_a_hostile_graph_serialised_by_tensorflows_proto_class(tmp_path):
+    """A graph as tf.train.Checkpoint(optimizer=, model=) lays it out, built with TensorFlow's message classes: children
+    in shuffled order, optimizer slot variables (m / v per weight), a registered_saver, has_checkpoint_values wrappers,
+    node ids that are not in path order, and unknown fields at every level.  The reader must still resolve every model
+    variable through the attribute path and ignore the rest."""
+    pb = _tf_graph_pb2()
+    dims = _small_dims()
+    rng = np.random.default_rng(3)
+    w = {n: rng.standard_normal(s).astype(np.float32) for n, s in W.variable_shapes(dims).items()}
+    paths = T.fact_object_paths(dims)
+    # build the trie with node ids assigned in a scrambled order
+    trie = {"": {}}
+    for path in list(paths.values()) + ["optimizer/iter", "optimizer/beta_1", "save_counter"]:
+        parts = path.split("/")
+        for i in range(len(parts)):
+            trie.setdefault("/".join(parts[:i + 1]), {})
+            trie["/".join(parts[:i])][parts[i]] = "/".join(parts[:i + 1])
+    ids = [p for p in trie if p != ""]
+    rng.shuffle(ids)
+    ids = [""] + ids                                                     # the root stays node 0
+    slot_base = len(ids)
+    index = {p: i for i, p in enumerate(ids)}
+    g = pb.TrackableObjectGraph()
+    for _ in range(slot_base):
+        g.nodes.add()
+    key_of = {}
+    for p, i in index.items():
+        node = g.nodes[i]
+        kids = list(trie[p].items())
+        rng.shuffle(kids)
+        for local, child in kids:
+            c = node.children.add()
+            c.node_id, c.local_name = index[child], local
+        if not trie[p] and p:                                            # a leaf: a variable
+            a = node.attributes.add()
+            a.name, a.full_name, a.checkpoint_key = "VARIABLE_VALUE", "some/graph/name:0", p + T.VAR_SUFFIX
+            key_of[p] = a.checkpoint_key
+            node.has_checkpoint_values.value = True
+    # optimizer slot variables hang off the optimizer node and point at extra nodes past the trie
+    opt = g.nodes[index["optimizer"]]
+    opt.registered_saver.name = "Custom>Saver"
+    opt.registered_saver.object_name = "optimizer"
+    slots = {}
+    for name, path in list(paths.items())[:6]:
+        for slot in ("m", "v"):
+            n = g.nodes.add()
+            a = n.attributes.add()
+            a.name = "VARIABLE_VALUE"
+            a.checkpoint_key = f"{path}/.OPTIMIZER_SLOT/optimizer/{slot}{T.VAR_SUFFIX}"
+            s = opt.slot_variables.add()
+            s.original_variable_node_id, s.slot_name, s.slot_variable_node_id = index[path], slot, len(g.nodes) - 1
+            slots[a.checkpoint_key] = np.zeros(w[name].shape, np.float32)
+    raw = g.SerializeToString()
+    # unknown fields: one appended to the graph, one spliced into the root node (field 15 varint, field 14 bytes)
+    root = g.nodes[0].SerializeToString() + T._tag(15, 0) + T._put_varint(99) + T._ld(14, b"future")
+    rest = b"".join(T._ld(1, n.SerializeToString()) for n in g.nodes[1:])
+    raw_hostile = T._ld(1, root) + rest + T._tag(9, 5) + (1234).to_bytes(4, "little")
+    assert pb.TrackableObjectGraph.FromString(raw_hostile).nodes[3] == g.nodes[3]      # still valid protobuf for TF
+    prefix = str(tmp_path / "ckpt-3")
+    bw = T.BundleWriter(prefix)
+    for name, path in paths.items():
+        bw.add(key_of[path], w[name])
+    for k, v in slots.items():
+        bw.add(k, v)
+    bw.add(key_of["optimizer/iter"], np.asarray(3, np.int64))
+    bw.add(key_of["optimizer/beta_1"], np.asarray(0.9, np.float32))
+    bw.add(key_of["save_counter"], np.asarray(1, np.int64))
+    bw.add_string_scalar(T.OBJECT_GRAPH_KEY, raw_hostile)
+    bw.close()
+    back = T.load_fact_weights(prefix, dims, verify=True)
+    assert set(back) == set(w)
+    for name in w:
+        np.testing.assert_array_equal(back[name], w[name])
+    b = T.Bundle(prefix)
+    nodes = b.object_graph()
+    assert len(nodes) == len(g.nodes)
+    with pytest.raises(KeyError):
+        b.variable_key("model/no_such_layer/kernel", nodes)
+    with pytest.raises(KeyError):
+        b.variable_key("model", nodes)                                   # an inner node is not a variable
+
+
+def test_string_tensor_checksums_are_verified(tmp_path):
+    prefix = str(tmp_path / "s")
+    bw = T.BundleWriter(prefix)
+    bw.add_string_scalar("k", b"hello object graph")
+    bw.close()
+    b = T.Bundle(prefix)
+    assert b.tensor("k").reshape(-1)[0] == b"hello object graph"
+    e = b.entries["k"]
+    # WriteStringTensor: the length enters the checksums as a uint32
+    assert e.size == 1 + 4 + 18
+    data = b._raw(e)
+    assert data[1:5] == struct.pack("<I", T.masked_crc(struct.pack("<I", 18)))
+    assert e.crc == T.masked_crc(struct.pack("<I", 18) + data[1:5] + b"hello object graph")
+    path = prefix + ".data-00000-of-00001"
+    raw = bytearray(open(path, "rb").read())
+    raw[-1] ^= 1
+    open(path, "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        T.Bundle(prefix).tensor("k")
+
+
+def test_tfrecord_framing_agrees_with_tensorboards_reader_and_writer(tmp_path):
+    """tensorboard (TensorFlow team's code, in the image) carries its own TFRecord writer and reader: frames written by
+    either side are read by the other, byte-identical for the same payloads."""
+    rw = pytest.importorskip("tensorboard.summary.writer.record_writer")
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    from mint_b200 import inputs
+    payloads = [b"", b"x", bytes(range(256)) * 9, np.random.default_rng(1).bytes(70001)]
+    ours, theirs = tmp_path / "ours.record", tmp_path / "theirs.record"
+    with inputs.TFRecordWriter(str(ours)) as wtr:
+        for p in payloads:
+            wtr.write(p)
+    f = open(theirs, "wb")
+    tw = rw.RecordWriter(f)
+    for p in payloads:
+        tw.write(p)
+    tw.close()
+    assert ours.read_bytes() == theirs.read_bytes()
+    assert list(inputs.read_tfrecords(str(theirs), verify_payload_crc=True)) == payloads
+    rd = pw.PyRecordReader_New(str(ours))
+    got = []
+    while True:
+        try:
+            rd.GetNext()
+        except Exception:
+            break
+        got.append(rd.record())
+    assert got == payloads
+    for p in payloads[1:]:
+        assert inputs.masked_crc(p) == pw.masked_crc32c(p)

@@ -12,12 +12,16 @@ from tests.helpers import make_config, oracle_dims
 
 pytestmark = pytest.mark.gpu
 
+SAME_OPERANDS_TOL = 1.5e-2     # vs the oracle on the same bf16-rounded operands (see _oracle_grads)
+
 SMALL = dict(d=64, heads=4, ff=128, layers=(1, 1, 2), motion_seq=12, audio_seq=20, motion_dim=225, out_dim=225)
 
 
-def _oracle_grads(dims, w, inp, t_len):
+def _oracle_grads(dims, w, inp, t_len, bf16_operands=False):
+    """fp64 autograd of the oracle; bf16_operands=True rounds every tensor-core operand (forward and backward) the way
+    the product's bf16 training path does, so what is left is accumulation / kernel error, not operand rounding."""
     wt = OT.to_torch(w, torch.float64, requires_grad=True)
-    pred = OT.call(wt, dims, inp)
+    pred = OT.call(wt, dims, inp, bf16_operands=bf16_operands)
     loss = OT.loss(torch.from_numpy(inp["target"][:, :t_len]), pred)
     loss.backward()
     return float(loss), {k: v.grad.numpy() for k, v in wt.items()}
@@ -52,6 +56,11 @@ def test_gradients_small_config(cuda, fact_lib):
     assert abs(loss - loss_ref) < 2e-2 * loss_ref, (loss, loss_ref)
     worst = _compare(m, gref, tol=6e-2)
     print("small config: loss", loss, loss_ref, "worst grad rel err", worst)
+    # against the oracle on the SAME bf16-rounded operands the tolerance is accumulation error, not bf16 rounding
+    loss_q, gq = _oracle_grads(dims, w, inp, 5, bf16_operands=True)
+    assert abs(loss - loss_q) < 2e-3 * loss_q, (loss, loss_q)
+    worst_q = _compare(m, gq, tol=SAME_OPERANDS_TOL, cos_tol=0.9999)
+    print("small config vs same-operand oracle: loss", loss, loss_q, "worst grad rel err", worst_q)
     # loss_scale scales the gradients, not the reported loss
     g1 = m.flat_gradients.clone()
     loss2 = float(m.forward_backward(tin, tin["target"], loss_scale=0.25))
@@ -71,6 +80,85 @@ def test_gradients_fact_v5(cuda, fact_lib):
     assert abs(loss - loss_ref) < 2e-2 * loss_ref, (loss, loss_ref)
     worst = _compare(m, gref, tol=8e-2, cos_tol=0.997)
     print("fact_v5: loss", loss, loss_ref, "worst grad rel err", worst)
+    loss_q, gq = _oracle_grads(dims, w, inp, 20, bf16_operands=True)
+    assert abs(loss - loss_q) < 2e-3 * loss_q, (loss, loss_q)
+    worst_q = _compare(m, gq, tol=SAME_OPERANDS_TOL, cos_tol=0.9999)
+    print("fact_v5 vs same-operand oracle: loss", loss, loss_q, "worst grad rel err", worst_q)
+
+
+def test_batch128_training_step_equals_the_batch2_step(cuda, fact_lib):
+    """The B = 128 step is where gemm_wgrad2_kernel (256x256 pair tiles, bulk reductions), the CTA-pair dgrad GEMMs
+    and the persistent LayerNorm-backward ring run inside fact_train_step.  No 128-clip oracle run is needed: the
+    loss is a mean, so 2 clips duplicated 64 times give the SAME loss and the SAME gradients as the 2 clips alone
+    (1/64 is a power of two: every bf16 rounding is identical), up to fp32 summation order."""
+    dims = oracle_dims()
+    w = O.init_weights(dims, seed=2)
+    two = O.synthetic_inputs(dims, batch=2, seed=11)
+    t2 = {k: torch.from_numpy(v).float() for k, v in two.items()}
+    m = FACTModel(make_config(), is_training=True, mode="bf16")
+    m.set_weights(w)
+    loss2 = float(m.forward_backward(t2, t2["target"]))
+    g2 = m.flat_gradients.clone()
+    idx = torch.arange(128) % 2
+    idx[5], idx[6] = 1, 0
+    # equal numbers of both clips, so the mean over the batch is the batch-2 mean
+    assert int((idx == 0).sum()) == 64
+    big = {k: v[idx].contiguous() for k, v in t2.items()}
+    loss128 = float(m.forward_backward(big, big["target"]))
+    g128 = m.flat_gradients.clone()
+    assert abs(loss128 - loss2) <= 2e-6 * abs(loss2), (loss128, loss2)
+    worst = (0.0, None)
+    for name, (off, cnt) in m._offsets.items():
+        a, b = g128[off:off + cnt].double(), g2[off:off + cnt].double()
+        nb = float(b.norm())
+        if nb < 1e-12:
+            assert float(a.norm()) < 1e-7, name
+            continue
+        err = float((a - b).norm()) / nb
+        worst = max(worst, (err, name))
+        assert err < 2e-3, (name, err)
+    print("batch 128 vs batch 2 gradients: worst rel err", worst)
+    # run to run: the loss is bitwise stable, gradients agree to fp32 reduction order (bulk reductions are unordered)
+    loss_again = float(m.forward_backward(big, big["target"]))
+    assert loss_again == loss128
+    again = m.flat_gradients
+    assert float((again - g128).double().norm()) <= 1e-5 * float(g128.double().norm())
+    assert torch.isfinite(again).all()
+
+
+def test_stage_events_and_device_side_clip(cuda, fact_lib):
+    """fact_train_step's stage events fire in bucket order and the staged slices cover the bucket; the on-device clip
+    (fact_sum_squares -> fact_clip_scale) equals tf.clip_by_global_norm."""
+    from mint_b200.trainer import clip_by_global_norm_
+    dims = oracle_dims(audio_dim=35, **SMALL)
+    m = FACTModel(make_config(**SMALL), is_training=True, mode="bf16")
+    inp = O.synthetic_inputs(dims, batch=2, seed=7, target_len=5)
+    tin = {k: torch.from_numpy(v).float() for k, v in inp.items()}
+    stages = m.gradient_stages()
+    assert stages[0][0] == 0 and sum(c for _, c in stages) == m.flat_parameters.numel()
+    assert all(stages[i][0] + stages[i][1] == stages[i + 1][0] for i in range(2))
+    names = list(m._offsets)
+    assert names[0].startswith("cross_modal_layer") and m._offsets["motion_transformer/layer_0/attn/norm/gamma"][0] == stages[1][0]
+    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    end = torch.cuda.Event(enable_timing=True)
+    for e in ev:
+        e.record()
+    m.forward_backward(tin, tin["target"])
+    ref = m.flat_gradients.clone()
+    m.forward_backward(tin, tin["target"], stage_events=ev)
+    end.record()
+    torch.cuda.synchronize()
+    assert ev[0].elapsed_time(ev[1]) >= 0 and ev[1].elapsed_time(end) >= 0
+    assert float((m.flat_gradients - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    g = m.flat_gradients
+    norm = float(g.double().norm())
+    before = g.clone()
+    clip_by_global_norm_(m, norm * 2)                       # above the norm: untouched
+    assert torch.equal(g, before)
+    clip_by_global_norm_(m, norm / 4)
+    torch.cuda.synchronize()
+    assert torch.allclose(g, before * 0.25, rtol=2e-6, atol=0)
+    assert abs(float(g.double().norm()) - norm / 4) < 1e-5 * norm
 
 
 def test_training_reduces_loss_and_matches_keras_adam_step(cuda, fact_lib):

@@ -26,6 +26,13 @@ class _FakeModel:
         return torch.tensor(float(self.rank + 1))
 
 
+class _StagedModel(_FakeModel):
+    """Adds the staged-reduce contract of FACTModel: three contiguous slices covering the bucket."""
+
+    def gradient_stages(self):
+        return [(0, 5), (5, 2), (7, 1)]
+
+
 class _FakeOpt:
     def __init__(self, model):
         self.model, self.iterations, self.seen = model, 0, None
@@ -47,6 +54,29 @@ def _worker(rank, world, port, q):
     loss = tr.train_step({"motion_input": 0, "audio_input": 0, "target": 1})
     # SUM over ranks of (rank+1)/world * base = mean over ranks = 1.5 * base
     ok = torch.allclose(opt.seen, 1.5 * torch.arange(1.0, 9.0)) and float(loss) == rank + 1 and model.global_step == 1
+    # staged reduce (three slices of the same bucket) must give the same sums as the single call
+    m2 = _StagedModel(rank)
+    o2 = _FakeOpt(m2)
+    SingleTaskTrainer([], "target", m2, optimizer=o2).train_step({"motion_input": 0, "target": 1})
+    ok = ok and torch.allclose(o2.seen, 1.5 * torch.arange(1.0, 9.0))
+    # clip BEFORE the sum (:180-183): each replica scales its own gradient to norm <= clip, then SUM
+    m3 = _StagedModel(rank)
+    o3 = _FakeOpt(m3)
+    SingleTaskTrainer([], "target", m3, optimizer=o3, grad_clip_norm=1.0).train_step({"motion_input": 0, "target": 1})
+    base = torch.arange(1.0, 9.0)
+    per = [(r + 1) * base / world for r in range(world)]
+    expect = sum(p * (1.0 / max(float(p.norm()), 1.0)) for p in per)
+    ok = ok and torch.allclose(o3.seen, expect, atol=1e-6)
+    # allreduce=False leaves the local gradient (bench.py's "exposed all-reduce" baseline)
+    m4 = _StagedModel(rank)
+    o4 = _FakeOpt(m4)
+    SingleTaskTrainer([], "target", m4, optimizer=o4, allreduce=False).train_step({"motion_input": 0, "target": 1})
+    ok = ok and torch.allclose(o4.seen, (rank + 1) * base / world)
+    # logged loss = Keras Mean of loss / num_replicas over replicas and steps (single_task_trainer.py:157-158, 189)
+    tr5 = SingleTaskTrainer([{"motion_input": 0, "target": 1}] * 2, "target", _StagedModel(rank),
+                            optimizer=_FakeOpt(_StagedModel(rank)))
+    logs = tr5.train(2)
+    ok = ok and abs(logs["training_loss"] - 0.75) < 1e-6
     shard = parallel.shard_clips(11, rank, world)
     gathered = [None] * world
     dist.all_gather_object(gathered, shard)

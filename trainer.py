@@ -57,6 +57,11 @@ def main():
                     help="also write every checkpoint in TensorFlow's format (ckpt-N.index / .data), readable by the "
                          "reference's tf.train.Checkpoint(model=...)")
     ap.add_argument("--data_npz", default="")
+    ap.add_argument("--products", default="bf16", choices=["bf16"],
+                    help="GEMM operand precision of the training step.  Only the bf16 product path exists (BASELINE.json "
+                         "configs[2]: 'training step bf16'): bf16 operands, fp32 accumulation, fp32 residual stream / "
+                         "statistics / gradients / master weights / Adam state.  The reference trains in fp32 "
+                         "throughout, so loss curves agree to bf16 rounding of the GEMM operands, not bit for bit")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -85,6 +90,9 @@ def main():
         model.set_weights(tf_checkpoint.load_fact_weights(args.init_tf_checkpoint, model.dims))
     if ckpts:                                                               # Controller restores the latest (orbit)
         sd = torch.load(os.path.join(args.model_dir, ckpts[-1]), map_location=dev)
+        if list(sd.get("names", model.variable_names())) != model.variable_names() or \
+                sd["flat_parameters"].numel() != model.flat_parameters.numel():
+            raise ValueError(f"{ckpts[-1]} was written for a different variable layout than this config builds")
         model.flat_parameters.copy_(sd["flat_parameters"])
         model.repack()
         opt.load_state_dict(sd["optimizer"])
@@ -103,6 +111,14 @@ def main():
                         tf_checkpoint.save_fact_weights(os.path.join(args.model_dir, "ckpt-%d" % opt.iterations),
                                                         {n: v.cpu().numpy() for n, v in model.get_weights().items()},
                                                         model.dims, step=opt.iterations)
+                        tf_prefixes = sorted((f[:-len(".index")] for f in os.listdir(args.model_dir)
+                                              if f.startswith("ckpt-") and f.endswith(".index")),
+                                             key=lambda n: int(n.split("-")[1]))
+                        for stale in tf_prefixes[:-args.max_to_keep]:            # CheckpointManager(max_to_keep=5)
+                            for f in os.listdir(args.model_dir):
+                                if f == stale + ".index" or f.startswith(stale + ".data-"):
+                                    os.remove(os.path.join(args.model_dir, f))
+                        tf_checkpoint.write_checkpoint_state(args.model_dir, tf_prefixes[-args.max_to_keep:])
                     old = sorted(f for f in os.listdir(args.model_dir)
                                  if f.startswith("ckpt-") and f.endswith(".pt"))[:-args.max_to_keep]
                     for f in old:
