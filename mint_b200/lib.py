@@ -79,7 +79,10 @@ SIGNATURES = {
     "fact_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), _i, _i]),
     "fact_forward": (_i, [C.POINTER(Dims), C.POINTER(Weights), _vp, _vp, _vp, _i, _vp, C.c_size_t, _i, _vp]),
     "fact_infer_auto_regressive": (_i, [C.POINTER(Dims), C.POINTER(Weights), _vp, _i, _vp, _i, _i, _i, _i, _vp,
-                                        _vp, C.c_size_t, _i, _i, _vp]),
+                                        _vp, C.c_size_t, _i, _i, _vp, _vp]),
+    "fact_ar_session_create": (_vp, []),
+    "fact_ar_session_destroy": (_i, [_vp]),
+    "fact_ar_session_graphs": (_i, [_vp]),
 }
 
 _lib = None
