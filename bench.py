@@ -334,6 +334,17 @@ def time_wgrad(model, batch, stream):
     return t, 2.0 * M * d * ff
 
 
+def gpu_topology(world):
+    """Link type between GPU0 and its peers as nvidia-smi reports it (NV18 = 18 NVLink-5 links through NVSwitch; PIX /
+    PHB / SYS = PCIe): explains an all-reduce bandwidth that is far from the NVLink figure."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        rows = [ln.split() for ln in out.splitlines() if ln.startswith("GPU0")]
+        return rows[0][1:1 + max(world, 1)] if rows else None
+    except Exception:
+        return None
+
+
 def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, max_over_ranks):
     """BASELINE.json configs[2] (N=1) / configs[3] (N>1): one sync data-parallel training step per "step" --
     fact_train_step (forward with saved activations, L2 motion loss, full backward), ONE logical all-reduce of the
@@ -355,9 +366,10 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
     out = {"config": {"workload": "fact_v5_deeper_t10_cm12 training step", "batch_per_gpu": B,
                       "global_batch": B * world, "products": "bf16 (fp32 accumulate, fp32 master weights / Adam state)",
                       "loss": "L2 motion loss on the first 20 frames", "optimizer": "Keras Adam",
-                      "parallelism": f"dp{world}: one all-reduce of the flat fp32 gradient bucket per step, issued as "
-                                     "3 slices (cross stack+head, motion encoder, audio encoder); the first two overlap "
-                                     "the rest of the backward on a side stream" if world > 1 else "single GPU"}}
+                      "parallelism": f"dp{world}: one logical all-reduce of the flat fp32 gradient bucket per step, "
+                                     "issued as contiguous slices in the order the backward finishes them (see "
+                                     "allreduce_slices_mb); all but the last overlap the rest of the backward on a side "
+                                     "stream" if world > 1 else "single GPU"}}
     with torch.cuda.stream(stream):
         batch_d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         dp = SingleTaskTrainer([], "target", model, optimizer=opt)
@@ -433,6 +445,10 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
         "frac_of_sustained_tensor_peak": TRAIN_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
         "allreduce_ms": ar_ms, "exposed_allreduce_ms": exposed, "ms_per_step_without_allreduce": ms_local,
         "grad_bucket_mb": model.flat_gradients.numel() * 4 / 1e6,
+        "allreduce_slices_mb": [round(c * 4 / 1e6, 1) for _, c, _ in dp._plan] if world > 1 and dp._plan else None,
+        "allreduce_busbw_gbs": (model.flat_gradients.numel() * 4 * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9
+                                if ar_ms else None),
+        "gpu_topology": gpu_topology(world) if rank == 0 else None,
         "e2e": {"ms_per_step": e2e_ms, "samples_per_s": world * B * 1e3 / e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches_per_step": int(launches) // K, "loss_first": first_loss, "loss_last": float(last),
@@ -744,10 +760,17 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries the ONE JSON line and nothing else: libraries that print to fd 1 (NCCL's version banner ...) go to
+    # stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

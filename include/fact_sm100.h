@@ -309,15 +309,19 @@ FACT_API size_t fact_train_workspace_bytes(const fact_dims* dims, int batch);
  * *loss_out = FACTModel.loss(target, pred) (unscaled), gradients of loss * loss_scale ACCUMULATED into `g` (zero the
  * gradient buffers first; loss_scale = 1 / num_replicas as in :157-158).  bf16 products, fp32 everything else.
  * target: [B, target_len, out_dim].
- * stage_events (optional, NULL = none): host array of two cudaEvent_t (either may be NULL).  [0] is recorded on `stream`
- * once the gradients of the cross-modal stack and the output head are final, [1] once those of the motion encoder and
- * its embeddings are too (the audio encoder's are final when the call's work completes).  They let a data-parallel host
- * start the cross-replica sum of those slices of its gradient bucket on another stream while the rest of the backward
- * runs (the bucket order of mint_b200/weights.py is cross stack + head, motion encoder, audio encoder). */
+ * stage_events (optional, NULL = none): host array of n_stage_events cudaEvent_t (entries may be NULL).  The backward
+ * finishes the gradient bucket in stages and records stage_events[i] on `stream` when stage i is final:
+ *   0                      the output head (out_w, out_b)
+ *   1 .. Lc                cross-modal layers Lc-1, Lc-2, ..., 0
+ *   Lc+1 .. Lc+Lm          motion layers Lm-1, ..., 0 (the last one also covers motion_pos and the motion embedding)
+ *   Lc+Lm+1 .. Lc+Lm+La    audio layers La-1, ..., 0 (the last one also covers audio_pos and the audio embedding; it is
+ *                          recorded after all work of the call)
+ * A data-parallel host starts the cross-replica sum of a finished slice of its gradient bucket on another stream while
+ * the rest of the backward runs (mint_b200/trainer.py). */
 FACT_API int fact_train_step(const fact_dims* dims, const fact_weights* w, const fact_grads* g, const float* motion,
                              const float* audio, const float* target, int target_len, int batch, float loss_scale,
                              float* loss_out, void* workspace, size_t workspace_bytes, void* const* stage_events,
-                             void* stream);
+                             int n_stage_events, void* stream);
 
 /* g[i] *= clip_norm / max(sqrt(*sum_squares), clip_norm) -- tf.clip_by_global_norm (single_task_trainer.py:180-183)
  * with the squared global norm read from DEVICE memory (fact_sum_squares output): no host synchronisation. */

@@ -260,7 +260,7 @@ extern "C" size_t fact_train_workspace_bytes(const fact_dims* dims, int batch) {
 extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, const fact_grads* g, const float* motion,
                                const float* audio, const float* target, int target_len, int batch, float loss_scale,
                                float* loss_out, void* workspace, size_t workspace_bytes,
-                               void* const* stage_events, void* stream) {
+                               void* const* stage_events, int n_stage_events, void* stream) {
   FACT_REQUIRE(dims && w && g && motion && audio && target && loss_out && batch > 0, FACT_ERR_BAD_SHAPE,
                "fact_train_step: bad arguments");
   const int d = dims->d_model, ns = dims->motion_seq + dims->audio_seq, od = dims->out_dim, odp = head_pad(od);
@@ -285,6 +285,14 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   const SavedLayer* Sc = Sa + dims->audio_layers;
   const int Mc = batch * ns;
   int rc;
+  // stage i of the backward is complete -> record stage_events[i] (see the header for the order)
+  int stage = 0;
+  auto stage_done = [&]() -> int {
+    const int i = stage++;
+    if (stage_events && i < n_stage_events && stage_events[i])
+      FACT_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(stage_events[i]), st));
+    return FACT_OK;
+  };
 
   // ------------------------------------------------------------------ forward (saves activations)
   if ((rc = embed_fwd_train(motion, w->motion_embed_w, w->motion_embed_b, w->motion_pos, Sm[0].x_in, ws.em_x, ws.em_w,
@@ -330,12 +338,15 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   e.out_f32 = ws.dy;
   e.ldo = d;
   if ((rc = bf16_gemm(ws.dpred_b, odp, w->out_w_kl, odp, Mc, d, odp, &e, st))) return rc;  // d xf = dpred . Wout^T
-  for (int l = dims->cross_layers - 1; l >= 0; --l)
+  if ((rc = stage_done())) return rc;  // stage 0: the output head
+  for (int l = dims->cross_layers - 1; l >= 0; --l) {
     if ((rc = layer_bwd(dims, w->cross_layers[l], g->cross_layers[l], Sc[l], batch, ns, ws.dy, ws,
                         l + 1 < dims->cross_layers, l > 0 ? g->cross_layers[l - 1].b2 : nullptr, st)))
       return rc;
-  // gradients of the cross-modal stack and the head are final: the host may start reducing that part of the bucket
-  if (stage_events && stage_events[0]) FACT_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(stage_events[0]), st));
+    // layer l's slice is final (its b2 sums were written by layer l+1's call; this call also wrote layer l-1's b2,
+    // which belongs to a slice that is reduced later)
+    if ((rc = stage_done())) return rc;
+  }
   // tf.concat backward (base_models.py:192-193): rows [0, motion_seq) -> motion encoder, the rest -> audio encoder
   if ((rc = slice_rows(ws.dy, ws.dym, static_cast<long long>(batch) * dims->motion_seq, d, dims->motion_seq, ns, 0, st)))
     return rc;
@@ -343,18 +354,24 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
                        dims->motion_seq, st)))
     return rc;
   // each encoder's first-layer LayerNorm backward also emits bf16(dy) and its column sums = the embedding bias gradient
-  for (int l = dims->motion_layers - 1; l >= 0; --l)
+  for (int l = dims->motion_layers - 1; l >= 0; --l) {
     if ((rc = layer_bwd(dims, w->motion_layers[l], g->motion_layers[l], Sm[l], batch, dims->motion_seq, ws.dym, ws,
                         l + 1 < dims->motion_layers, l > 0 ? g->motion_layers[l - 1].b2 : g->motion_embed_b, st)))
       return rc;
+    if (l > 0 && (rc = stage_done())) return rc;
+  }
   if ((rc = embed_bwd_train(ws.em_x, ws.em_kp, ws.dym, ws.dy_b, g->motion_embed_w, g->motion_pos, batch,
                             dims->motion_seq, dims->motion_dim, d, st)))
     return rc;
-  if (stage_events && stage_events[1]) FACT_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(stage_events[1]), st));
-  for (int l = dims->audio_layers - 1; l >= 0; --l)
+  if ((rc = stage_done())) return rc;  // motion layer 0 + its position table and LinearEmbedding
+  for (int l = dims->audio_layers - 1; l >= 0; --l) {
     if ((rc = layer_bwd(dims, w->audio_layers[l], g->audio_layers[l], Sa[l], batch, dims->audio_seq, ws.dya, ws,
                         l + 1 < dims->audio_layers, l > 0 ? g->audio_layers[l - 1].b2 : g->audio_embed_b, st)))
       return rc;
-  return embed_bwd_train(ws.ea_x, ws.ea_kp, ws.dya, ws.dy_b, g->audio_embed_w, g->audio_pos, batch, dims->audio_seq,
-                         dims->audio_dim, d, st);
+    if (l > 0 && (rc = stage_done())) return rc;
+  }
+  if ((rc = embed_bwd_train(ws.ea_x, ws.ea_kp, ws.dya, ws.dy_b, g->audio_embed_w, g->audio_pos, batch, dims->audio_seq,
+                            dims->audio_dim, d, st)))
+    return rc;
+  return stage_done();  // audio layer 0 + its position table and LinearEmbedding: the whole bucket is final
 }

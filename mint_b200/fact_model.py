@@ -369,23 +369,50 @@ class FACTModel:
             G["audio_pos_embedding"].data_ptr(),
             G["cross_modal_layer/output/kernel"].data_ptr(), G["cross_modal_layer/output/bias"].data_ptr())
 
-    def gradient_stages(self) -> list[tuple[int, int]]:
-        """(offset, count) slices of `flat_gradients` in the order the backward pass finishes them: cross-modal stack +
-        head, motion encoder (+ embeddings), audio encoder (+ embeddings).  Contiguous and covering the whole bucket
-        (the variable order of mint_b200/weights.py), 16-byte aligned."""
-        names = list(self._offsets)
-        first_motion = next(i for i, n in enumerate(names) if n.startswith("motion_"))
-        first_audio = next(i for i, n in enumerate(names) if n.startswith("audio_"))
-        assert first_motion < first_audio and all(n.startswith("cross_modal_layer") for n in names[:first_motion])
-        a, b = self._offsets[names[first_motion]][0], self._offsets[names[first_audio]][0]
+    def gradient_stages(self) -> list[tuple[int, int, int]]:
+        """(offset, count, event) slices of `flat_gradients` in the order fact_train_step finishes them; `event` is the
+        index of the stage event (include/fact_sm100.h) after which the slice is final: the head, cross layers top to
+        bottom, motion layers top to bottom, audio layers likewise.  A modality's last event covers two ranges (its
+        layer 0, and its position table + LinearEmbedding, which sit behind the other layers in the bucket).  Slices
+        are contiguous, 16-byte aligned and together cover the bucket."""
+        d = self.dims
+        first = lambda prefix: self._offsets[next(n for n in self._offsets if n.startswith(prefix))][0]
         total = self._flat.numel()
-        return [(0, a), (a, b - a), (b, total - b)]
+        cuts = {("head", 0): first("cross_modal_layer/output/"), ("motion_tail", 0): first("motion_pos_embedding"),
+                ("audio_tail", 0): first("audio_pos_embedding")}
+        for i in range(d.cross_layers):
+            cuts[("cross", i)] = first(f"cross_modal_layer/transformer/layer_{i}/")
+        for i in range(d.motion.layers):
+            cuts[("motion", i)] = first(f"motion_transformer/layer_{i}/")
+        for i in range(d.audio.layers):
+            cuts[("audio", i)] = first(f"audio_transformer/layer_{i}/")
+        order = sorted(cuts.values()) + [total]
+        end = {off: order[i + 1] for i, off in enumerate(order[:-1])}
+        span = lambda key: (cuts[key], end[cuts[key]] - cuts[key])
+        stages = [(*span(("head", 0)), 0)]
+        ev = 1
+        for i in reversed(range(d.cross_layers)):
+            stages.append((*span(("cross", i)), ev))
+            ev += 1
+        for name, layers in (("motion", d.motion.layers), ("audio", d.audio.layers)):
+            for i in reversed(range(layers)):
+                stages.append((*span((name, i)), ev))
+                if i == 0:
+                    stages.append((*span((name + "_tail", 0)), ev))
+                ev += 1
+        assert sum(c for _, c, _ in stages) == total and ev == self.num_gradient_stage_events
+        return stages
+
+    @property
+    def num_gradient_stage_events(self) -> int:
+        d = self.dims
+        return 1 + d.cross_layers + d.motion.layers + d.audio.layers
 
     def forward_backward(self, inputs: dict, target, loss_scale: float = 1.0, stage_events=None) -> torch.Tensor:
         """One replica's forward + backward (single_task_trainer.py:145-178): returns FACTModel.loss(target, pred)
         and leaves d(loss * loss_scale)/d(variable) in `flat_gradients` (zeroed first).  bf16 products, fp32 stats.
-        stage_events: optional pair of torch.cuda.Event recorded when the first / second slice of gradient_stages()
-        is final (the third is final when the call's work completes)."""
+        stage_events: optional list of torch.cuda.Event (entries may be None), recorded as the stages of the backward
+        finish (order: include/fact_sm100.h, fact_train_step; see gradient_stages / gradient_stage_events)."""
         self._ensure_training_state()
         d = self.dims
         motion = self._to_dev(inputs["motion_input"], d.motion.feature_dim, "motion_input")
@@ -405,13 +432,14 @@ class FACTModel:
         self._grad_flat.zero_()
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
-            ev = None
+            ev, n_ev = None, 0
             if stage_events is not None:
-                ev = (C.c_void_p * 2)(*[e.cuda_event if e is not None else None for e in stage_events])
+                n_ev = len(stage_events)
+                ev = (C.c_void_p * n_ev)(*[e.cuda_event if e is not None else None for e in stage_events])
             lib.check(self._lib.fact_train_step(
                 C.byref(self._cdims), C.byref(self._cw), C.byref(self._cg), motion.data_ptr(), audio.data_ptr(),
                 target.data_ptr(), target.shape[1], batch, float(loss_scale), loss.data_ptr(), base,
-                self._train_ws.numel() - (base - self._train_ws.data_ptr()), ev, st), "fact_train_step")
+                self._train_ws.numel() - (base - self._train_ws.data_ptr()), ev, n_ev, st), "fact_train_step")
         return loss
 
     def get_metrics(self, eval_config):

@@ -4,12 +4,13 @@ Same step semantics: pop the label, forward, `loss / num_replicas`, gradients, o
 clip_by_global_norm BEFORE the cross-replica sum (single_task_trainer.py:180-183), one SUM all-reduce of all gradients
 (what MirroredStrategy does inside apply_gradients, :186-187), Adam.  One process per GPU.
 
-The cross-replica sum is ONE logical all-reduce of the model's flat gradient bucket, issued in the three contiguous
-slices the backward pass finishes in turn (FACTModel.gradient_stages: cross-modal stack + head, motion encoder, audio
-encoder).  The first two run on a side stream behind the events fact_train_step records, so they overlap the rest of
-the backward; only the last (smallest) slice is exposed.  Clipping needs the norm of the whole gradient before any
-slice may be summed, so with grad_clip_norm > 0 the reduce is a single call after the backward; the clip factor is
-computed and applied on the device (no host synchronisation).
+The cross-replica sum is ONE logical all-reduce of the model's flat gradient bucket, issued as a few contiguous slices
+in the order the backward pass finishes them (FACTModel.gradient_stages: head, cross layers top to bottom, motion
+encoder, audio encoder; adjacent layers are merged into `allreduce_chunks` slices of similar size).  All but the last
+run on a side stream behind the events fact_train_step records, so they overlap the rest of the backward; only the
+last slice (the bottom layer of the audio encoder + its embeddings, 6 % of the bucket) is exposed.  Clipping needs the
+norm of the whole gradient before any slice may be summed, so with grad_clip_norm > 0 the reduce is a single call after
+the backward; the clip factor is computed and applied on the device (no host synchronisation).
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ import torch.distributed as dist
 class SingleTaskTrainer:
     def __init__(self, train_dataset, label_key, model, loss_fn=None, optimizer=None, metrics=None,
                  trainer_options=None, summary_fn=None, grad_clip_norm: float = 0.0, overlap_allreduce: bool = True,
-                 allreduce: bool = True):
+                 allreduce: bool = True, allreduce_chunks: int = 8):
         """train_dataset: iterable of dict batches (torch / numpy); label_key: 'target' (trainer.py:157).
         allreduce=False skips the cross-replica sum (bench.py uses it to measure how much of it is exposed)."""
         self.train_dataset = train_dataset
@@ -40,12 +41,16 @@ class SingleTaskTrainer:
         self._comm = None
         self._events = None
         self._sumsq = None
+        self._plan = plan_allreduce(model.gradient_stages(), allreduce_chunks) if self.overlap else None
         dev = getattr(model, "device", torch.device("cpu"))
         if self.world > 1 and self.overlap and dev.type == "cuda":
             self._comm = torch.cuda.Stream(dev)
-            self._events = [torch.cuda.Event(), torch.cuda.Event()]
+            wanted = {ev for _, _, ev in self._plan[:-1]}
+            self._events = [torch.cuda.Event() if i in wanted else None
+                            for i in range(model.num_gradient_stage_events)]
             for e in self._events:
-                e.record(torch.cuda.current_stream(dev))     # creates the cudaEvent_t the C ABI re-records
+                if e is not None:
+                    e.record(torch.cuda.current_stream(dev))     # creates the cudaEvent_t the C ABI re-records
 
     def train_loop_begin(self):
         self.train_loss, self._steps = 0.0, 0
@@ -63,18 +68,17 @@ class SingleTaskTrainer:
         if clip:                                                                # :180-183, per replica, before the sum
             clip_by_global_norm_(self.model, self.grad_clip_norm, self)
         if staged:                                                              # :186-187 (cross-replica SUM)
-            stages = self.model.gradient_stages()
             if self._comm is not None:
                 cur = torch.cuda.current_stream(grads.device)
                 with torch.cuda.stream(self._comm):
-                    for (off, cnt), ev in zip(stages[:2], self._events):
-                        self._comm.wait_event(ev)
+                    for off, cnt, ev in self._plan[:-1]:
+                        self._comm.wait_event(self._events[ev])
                         dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)
-                off, cnt = stages[2]
+                off, cnt, _ = self._plan[-1]
                 dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)     # behind the whole backward
                 cur.wait_stream(self._comm)
             else:
-                for off, cnt in stages:
+                for off, cnt, _ in self._plan:
                     dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)
         elif reduce:
             dist.all_reduce(grads, op=dist.ReduceOp.SUM)
@@ -108,6 +112,30 @@ class SingleTaskTrainer:
         dt = time.perf_counter() - self._t0
         return {"training_loss": mean, "task_loss": mean, "regularization_loss": 0.0,
                 "learning_rate": self.optimizer.current_lr(), "steps_per_second": n / dt if dt > 0 else float("nan")}
+
+
+def plan_allreduce(stages, chunks: int):
+    """Merge the backward's stages [(offset, count, event)] (completion order) into at most ~`chunks` contiguous slices
+    [(offset, count, event)] of similar size; a merged slice waits for the LAST event of its members.  Only slices that
+    touch in memory are merged, and the slices whose event is the final one stay apart from the rest (they are the
+    exposed tail, so they are kept as small as the stages allow) -- but are merged with each other when adjacent."""
+    total = sum(c for _, c, _ in stages)
+    last_ev = stages[-1][2]
+    target = total / max(1, chunks)
+    out = []
+    for off, cnt, ev in stages:
+        if out:
+            o, c, e = out[-1]
+            touching = o + c == off or off + cnt == o
+            same_side = (e == last_ev) == (ev == last_ev)
+            if touching and same_side and (c < target or ev == last_ev):
+                out[-1] = (min(o, off), c + cnt, max(e, ev))
+                continue
+        out.append((off, cnt, ev))
+    # the final-event slices go last, as ONE call when they touch, else in bucket order
+    tail = sorted(s for s in out if s[2] == last_ev)
+    head = [s for s in out if s[2] != last_ev]
+    return head + tail
 
 
 def clip_by_global_norm_(model, clip_norm: float, owner=None) -> None:

@@ -12,7 +12,7 @@ from tests.helpers import make_config, oracle_dims
 
 pytestmark = pytest.mark.gpu
 
-SAME_OPERANDS_TOL = 1.5e-2     # vs the oracle on the same bf16-rounded operands (see _oracle_grads)
+SAME_OPERANDS_TOL = 8e-3       # vs the oracle on the same bf16-rounded operands (see _oracle_grads)
 
 SMALL = dict(d=64, heads=4, ff=128, layers=(1, 1, 2), motion_seq=12, audio_seq=20, motion_dim=225, out_dim=225)
 
@@ -54,7 +54,7 @@ def test_gradients_small_config(cuda, fact_lib):
     tin = {k: torch.from_numpy(v).float() for k, v in inp.items()}
     loss = float(m.forward_backward(tin, tin["target"], loss_scale=1.0))
     assert abs(loss - loss_ref) < 2e-2 * loss_ref, (loss, loss_ref)
-    worst = _compare(m, gref, tol=6e-2)
+    worst = _compare(m, gref, tol=2e-2)
     print("small config: loss", loss, loss_ref, "worst grad rel err", worst)
     # against the oracle on the SAME bf16-rounded operands the tolerance is accumulation error, not bf16 rounding
     loss_q, gq = _oracle_grads(dims, w, inp, 5, bf16_operands=True)
@@ -78,7 +78,7 @@ def test_gradients_fact_v5(cuda, fact_lib):
     tin = {k: torch.from_numpy(v).float() for k, v in inp.items()}
     loss = float(m.forward_backward(tin, tin["target"]))
     assert abs(loss - loss_ref) < 2e-2 * loss_ref, (loss, loss_ref)
-    worst = _compare(m, gref, tol=8e-2, cos_tol=0.997)
+    worst = _compare(m, gref, tol=2e-2, cos_tol=0.9995)
     print("fact_v5: loss", loss, loss_ref, "worst grad rel err", worst)
     loss_q, gq = _oracle_grads(dims, w, inp, 20, bf16_operands=True)
     assert abs(loss - loss_q) < 2e-3 * loss_q, (loss, loss_q)
@@ -89,8 +89,12 @@ def test_gradients_fact_v5(cuda, fact_lib):
 def test_batch128_training_step_equals_the_batch2_step(cuda, fact_lib):
     """The B = 128 step is where gemm_wgrad2_kernel (256x256 pair tiles, bulk reductions), the CTA-pair dgrad GEMMs
     and the persistent LayerNorm-backward ring run inside fact_train_step.  No 128-clip oracle run is needed: the
-    loss is a mean, so 2 clips duplicated 64 times give the SAME loss and the SAME gradients as the 2 clips alone
-    (1/64 is a power of two: every bf16 rounding is identical), up to fp32 summation order."""
+    loss is a mean, so 2 clips duplicated 64 times have the SAME loss and gradients as the 2 clips alone (1/64 is a
+    power of two, so the scaling itself is exact).  What differs is the kernel path (tile shapes, fp32 summation
+    order): last-bit differences before a bf16 store flip a rounding now and then, and those flips compound through
+    ~100 rounding points -- measured on B200: median 2e-4 per tensor, worst 2.6e-3 on the deepest tensors (motion
+    layer 0 / embedding), the same for 4, 8, 16, 32 and 128 clips (scripts/experiments/diag_b128.py).  A wrong tile,
+    a dropped token slice or a mis-scaled reduction would show as >= 1e-2."""
     dims = oracle_dims()
     w = O.init_weights(dims, seed=2)
     two = O.synthetic_inputs(dims, batch=2, seed=11)
@@ -107,7 +111,7 @@ def test_batch128_training_step_equals_the_batch2_step(cuda, fact_lib):
     loss128 = float(m.forward_backward(big, big["target"]))
     g128 = m.flat_gradients.clone()
     assert abs(loss128 - loss2) <= 2e-6 * abs(loss2), (loss128, loss2)
-    worst = (0.0, None)
+    worst, errs = (0.0, None), []
     for name, (off, cnt) in m._offsets.items():
         a, b = g128[off:off + cnt].double(), g2[off:off + cnt].double()
         nb = float(b.norm())
@@ -116,8 +120,11 @@ def test_batch128_training_step_equals_the_batch2_step(cuda, fact_lib):
             continue
         err = float((a - b).norm()) / nb
         worst = max(worst, (err, name))
-        assert err < 2e-3, (name, err)
-    print("batch 128 vs batch 2 gradients: worst rel err", worst)
+        errs.append(err)
+        assert err < 6e-3, (name, err)
+    errs.sort()
+    print("batch 128 vs batch 2 gradients: worst rel err", worst, "median", errs[len(errs) // 2])
+    assert errs[len(errs) // 2] < 1e-3
     # run to run: the loss is bitwise stable, gradients agree to fp32 reduction order (bulk reductions are unordered)
     loss_again = float(m.forward_backward(big, big["target"]))
     assert loss_again == loss128
@@ -135,21 +142,33 @@ def test_stage_events_and_device_side_clip(cuda, fact_lib):
     inp = O.synthetic_inputs(dims, batch=2, seed=7, target_len=5)
     tin = {k: torch.from_numpy(v).float() for k, v in inp.items()}
     stages = m.gradient_stages()
-    assert stages[0][0] == 0 and sum(c for _, c in stages) == m.flat_parameters.numel()
-    assert all(stages[i][0] + stages[i][1] == stages[i + 1][0] for i in range(2))
-    names = list(m._offsets)
-    assert names[0].startswith("cross_modal_layer") and m._offsets["motion_transformer/layer_0/attn/norm/gamma"][0] == stages[1][0]
-    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    total = m.flat_parameters.numel()
+    spans = sorted((o, o + c) for o, c, _ in stages)
+    assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    n_ev = m.num_gradient_stage_events
+    assert [e for _, _, e in stages] == sorted(e for _, _, e in stages) and stages[-1][2] == n_ev - 1
+    head_off = m._offsets["cross_modal_layer/output/kernel"][0]
+    assert stages[0][:2] == (head_off, m._offsets["motion_transformer/layer_0/attn/norm/gamma"][0] - head_off)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
     end = torch.cuda.Event(enable_timing=True)
     for e in ev:
         e.record()
     m.forward_backward(tin, tin["target"])
     ref = m.flat_gradients.clone()
+    # every slice must already hold its final value when its event fires: snapshot each slice on a side stream that
+    # only waits for that event, while the main stream keeps running the backward
+    side = torch.cuda.Stream()
+    snaps = []
     m.forward_backward(tin, tin["target"], stage_events=ev)
     end.record()
+    with torch.cuda.stream(side):
+        for off, cnt, e in stages:
+            side.wait_event(ev[e])
+            snaps.append(m.flat_gradients[off:off + cnt].clone())
     torch.cuda.synchronize()
-    assert ev[0].elapsed_time(ev[1]) >= 0 and ev[1].elapsed_time(end) >= 0
-    assert float((m.flat_gradients - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    assert all(ev[i].elapsed_time(ev[i + 1]) >= 0 for i in range(n_ev - 1)) and ev[-1].elapsed_time(end) >= 0
+    for (off, cnt, _), snap in zip(stages, snaps):
+        assert float((snap - ref[off:off + cnt]).abs().max()) <= 1e-6 * float(ref.abs().max())
     g = m.flat_gradients
     norm = float(g.double().norm())
     before = g.clone()

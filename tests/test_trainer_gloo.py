@@ -29,8 +29,11 @@ class _FakeModel:
 class _StagedModel(_FakeModel):
     """Adds the staged-reduce contract of FACTModel: three contiguous slices covering the bucket."""
 
+    num_gradient_stage_events = 4
+
     def gradient_stages(self):
-        return [(0, 5), (5, 2), (7, 1)]
+        # (offset, count, event) in completion order: not in memory order, and the last event covers two ranges
+        return [(3, 2, 0), (0, 3, 1), (6, 1, 2), (5, 1, 3), (7, 1, 3)]
 
 
 class _FakeOpt:
@@ -99,6 +102,24 @@ def test_two_rank_gloo():
     for p in procs:
         p.join(30)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_allreduce_plan_merges_touching_stages_and_keeps_the_tail_small():
+    from mint_b200.trainer import plan_allreduce
+    stages = [(100, 10, 0)] + [(100 - 20 * (i + 1), 20, i + 1) for i in range(5)] + [(130, 20, 6), (110, 20, 7), (150, 5, 7)]
+    total = sum(c for _, c, _ in stages)
+    for chunks in (1, 3, 8, 100):
+        plan = plan_allreduce(stages, chunks)
+        covered = sorted((o, o + c) for o, c, _ in plan)
+        assert covered[0][0] == 0 and covered[-1][1] == 155 and sum(c for _, c, _ in plan) == total
+        assert all(a[1] <= b[0] for a, b in zip(covered, covered[1:]))          # disjoint
+        for o, c, e in plan:                                                     # a slice waits for its last member
+            assert e == max(ev for so, sc, ev in stages if so >= o and so + sc <= o + c)
+        assert [e for _, _, e in plan] == sorted(e for _, _, e in plan)          # issue order = completion order
+        tail = [p for p in plan if p[2] == 7]
+        assert sum(c for _, c, _ in tail) == 25                                  # the exposed tail is only the last stage
+    assert len(plan_allreduce(stages, 100)) == len(stages)
+    assert len(plan_allreduce(stages, 1)) <= 4
 
 
 def test_shard_clips_single_process():
