@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
                                                        bf16* __restrict__ lo, int rows, int d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const int nv = d >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
@@ -265,7 +267,71 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(SimtArgs p) {
   }
 }
 
+// LinearEmbedding at decode batch sizes (a few hundred rows, K = 225 / 35): the tiled kernel above puts the whole
+// problem on ~26 blocks that each walk K in 15 synchronised steps (51 us at batch 1, on the critical path of every
+// AR frame).  Here a block owns 8 rows x 64 columns and its 256 threads split K four ways, so ~200 blocks run
+// ~60-long FMA chains with coalesced weight loads; the four partial sums meet in shared memory in a fixed order.
+constexpr int ER_ROWS = 8, ER_COLS = 64, ER_KG = 4;
+__global__ void __launch_bounds__(256) embed_rows_kernel(SimtArgs p) {
+  extern __shared__ float er_smem[];   // [ER_ROWS][k] inputs, then [ER_KG - 1][ER_ROWS][ER_COLS] partials
+  float* xs = er_smem;
+  float* part = er_smem + ER_ROWS * p.k;
+  const int tx = threadIdx.x & (ER_COLS - 1), kg = threadIdx.x / ER_COLS;
+  const int m0 = blockIdx.y * ER_ROWS, col = blockIdx.x * ER_COLS + tx;
+  pdl_trigger();
+  pdl_wait();   // the step counter and the motion history row of the previous frame come from the previous graph launch
+  const int start = p.step_ptr ? *p.step_ptr : 0;
+  for (int e = threadIdx.x; e < ER_ROWS * p.k; e += 256) {
+    const int r = e / p.k, k = e % p.k, row = m0 + r;
+    float a = 0.f;
+    if (row < p.m)
+      a = p.a_f32[static_cast<size_t>(row / p.a_seq) * p.a_batch_stride +
+                  static_cast<size_t>(start + row % p.a_seq) * p.lda + k];
+    xs[e] = a;
+  }
+  __syncthreads();
+  const int kper = (p.k + ER_KG - 1) / ER_KG;
+  const int k0 = kg * kper, k1 = min(p.k, k0 + kper);
+  float acc[ER_ROWS];
+#pragma unroll
+  for (int r = 0; r < ER_ROWS; ++r) acc[r] = 0.f;
+  if (col < p.n) {
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+      const float w = __ldg(p.w + static_cast<size_t>(k) * p.n + col);
+#pragma unroll
+      for (int r = 0; r < ER_ROWS; ++r) acc[r] = fmaf(xs[r * p.k + k], w, acc[r]);
+    }
+  }
+  if (kg > 0) {
+#pragma unroll
+    for (int r = 0; r < ER_ROWS; ++r) part[((kg - 1) * ER_ROWS + r) * ER_COLS + tx] = acc[r];
+  }
+  __syncthreads();
+  if (kg == 0 && col < p.n) {
+    const float b = p.bias ? p.bias[col] : 0.f;
+#pragma unroll
+    for (int r = 0; r < ER_ROWS; ++r) {
+      const int row = m0 + r;
+      if (row >= p.m) break;
+      float x = acc[r];
+#pragma unroll
+      for (int g = 0; g < ER_KG - 1; ++g) x += part[(g * ER_ROWS + r) * ER_COLS + tx];
+      x += b;
+      if (p.pos) x += p.pos[static_cast<size_t>(row % p.pos_seq) * p.n + col];
+      p.out_f32[static_cast<size_t>(row) * p.ldo + col] = x;
+    }
+  }
+}
+
 static int launch_simt(const SimtArgs& p, cudaStream_t st) {
+  if (p.a_f32 && p.a_seq > 0 && p.kind == FACT_EPI_BIAS_F32 && p.seq_in == 0 && p.m <= 1024 && p.k <= 1024) {
+    dim3 grid((p.n + ER_COLS - 1) / ER_COLS, (p.m + ER_ROWS - 1) / ER_ROWS);
+    const size_t smem = (static_cast<size_t>(ER_ROWS) * p.k + (ER_KG - 1) * ER_ROWS * ER_COLS) * sizeof(float);
+    FACT_CUDA_CHECK(launch_k(embed_rows_kernel, grid, dim3(256), smem, st, true, p));
+    FACT_LAUNCH_CHECK("embed_rows_kernel launch");
+    return FACT_OK;
+  }
   if (p.m >= 1024 && p.n >= 128) {
     dim3 grid((p.n + 127) / 128, (p.m + 127) / 128);
     gemm_f32_kernel<128, 128><<<grid, 256, 0, st>>>(p);
@@ -326,35 +392,38 @@ int gemm_simt_split(const void* a_hi, const void* a_lo, int lda, const float* w_
 }
 
 // ------------------------------------------------------------------------------------------- head on one row / sample
-__global__ void __launch_bounds__(1024) head_rows_kernel(const float* __restrict__ x, long long row_stride,
-                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                         float* __restrict__ out, long long out_batch_stride,
-                                                         const int* __restrict__ step_ptr, int d, int out_dim) {
-  // one block per clip; 4 groups of 256 threads split the reduction dimension (the serial 800-long FMA chain of a
-  // single group made this 144 us at batch 1), partials meet in shared memory
-  extern __shared__ float xs[];          // [d] input row, then [3][out_dim_pad] partials
+constexpr int HR_COLS = 32, HR_KG = 8;
+__global__ void __launch_bounds__(256) head_rows_kernel(const float* __restrict__ x, long long row_stride,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ out, long long out_batch_stride,
+                                                        const int* __restrict__ step_ptr, int d, int out_dim) {
+  // block (b, c) = clip b, 32 output columns; 8 groups of 32 threads split the reduction dimension (100-long FMA
+  // chains with coalesced weight loads) and meet in shared memory in a fixed order.  One block per clip with 4
+  // groups was 21 us at batch 1 (800 / 4 dependent loads per thread on a single SM).
+  extern __shared__ float xs[];          // [d] input row, then [HR_KG - 1][HR_COLS] partials
   const int b = blockIdx.x;
-  const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
+  const int grp = threadIdx.x / HR_COLS, t = threadIdx.x % HR_COLS;
   const float* xr = x + static_cast<size_t>(b) * row_stride * d;
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < d; i += blockDim.x) xs[i] = xr[i];
   __syncthreads();
   float* part = xs + d;
   const int step = step_ptr ? *step_ptr : 0;
-  const int k0 = grp * ((d + 3) / 4), k1 = min(d, k0 + (d + 3) / 4);
-  for (int j0 = 0; j0 < out_dim; j0 += 256) {
-    const int j = j0 + t;
-    float acc = 0.f;
-    if (j < out_dim) {
-#pragma unroll 8
-      for (int k = k0; k < k1; ++k) acc = fmaf(xs[k], __ldg(w + static_cast<size_t>(k) * out_dim + j), acc);
-    }
-    if (grp > 0 && j < out_dim) part[(grp - 1) * 256 + t] = acc;
-    __syncthreads();
-    if (grp == 0 && j < out_dim) {
-      acc += part[t] + part[256 + t] + part[512 + t];
-      out[static_cast<size_t>(b) * out_batch_stride + static_cast<size_t>(step) * out_dim + j] = acc + bias[j];
-    }
-    __syncthreads();
+  const int kper = (d + HR_KG - 1) / HR_KG;
+  const int k0 = grp * kper, k1 = min(d, k0 + kper);
+  const int j = blockIdx.y * HR_COLS + t;
+  float acc = 0.f;
+  if (j < out_dim) {
+#pragma unroll 10
+    for (int k = k0; k < k1; ++k) acc = fmaf(xs[k], __ldg(w + static_cast<size_t>(k) * out_dim + j), acc);
+  }
+  if (grp > 0) part[(grp - 1) * HR_COLS + t] = acc;
+  __syncthreads();
+  if (grp == 0 && j < out_dim) {
+#pragma unroll
+    for (int g = 0; g < HR_KG - 1; ++g) acc += part[g * HR_COLS + t];
+    out[static_cast<size_t>(b) * out_batch_stride + static_cast<size_t>(step) * out_dim + j] = acc + bias[j];
   }
 }
 
@@ -410,7 +479,11 @@ __global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__
 }
 
 __global__ void step_set_kernel(int* p, int v) { *p = v; }
-__global__ void step_inc_kernel(int* p) { *p += 1; }
+__global__ void step_inc_kernel(int* p) {
+  pdl_trigger();
+  pdl_wait();
+  *p += 1;
+}
 
 int step_set(int* p, int v, cudaStream_t st) {
   step_set_kernel<<<1, 1, 0, st>>>(p, v);
@@ -418,7 +491,7 @@ int step_set(int* p, int v, cudaStream_t st) {
   return FACT_OK;
 }
 int step_inc(int* p, cudaStream_t st) {
-  step_inc_kernel<<<1, 1, 0, st>>>(p);
+  FACT_CUDA_CHECK(launch_k(step_inc_kernel, dim3(1), dim3(1), 0, st, true, p));
   FACT_LAUNCH_CHECK("step_inc_kernel");
   return FACT_OK;
 }
@@ -441,12 +514,13 @@ extern "C" int fact_layernorm_split(const float* x, const float* gamma, const fl
                FACT_ERR_BAD_ALIGN, "fact_layernorm_split: x must be 16-B, y 8-B aligned");
   const int grid = (rows + 7) / 8;
   cudaStream_t st = as_stream(stream);
+  const float* no_f = nullptr;
   if (gamma)
-    ln_split_kernel<true><<<grid, 256, 0, st>>>(x, gamma, beta, static_cast<bf16*>(y_hi), static_cast<bf16*>(y_lo),
-                                                rows, d);
+    FACT_CUDA_CHECK(launch_k(ln_split_kernel<true>, dim3(grid), dim3(256), 0, st, true, x, gamma, beta,
+                             static_cast<bf16*>(y_hi), static_cast<bf16*>(y_lo), rows, d));
   else
-    ln_split_kernel<false><<<grid, 256, 0, st>>>(x, nullptr, nullptr, static_cast<bf16*>(y_hi),
-                                                 static_cast<bf16*>(y_lo), rows, d);
+    FACT_CUDA_CHECK(launch_k(ln_split_kernel<false>, dim3(grid), dim3(256), 0, st, true, x, no_f, no_f,
+                             static_cast<bf16*>(y_hi), static_cast<bf16*>(y_lo), rows, d));
   FACT_LAUNCH_CHECK("ln_split_kernel launch");
   return FACT_OK;
 }
@@ -569,8 +643,10 @@ extern "C" int fact_head_rows(const float* x, long long row_stride, const float*
                               int out_dim, void* stream) {
   FACT_REQUIRE(x && w_keras && bias && out, FACT_ERR_BAD_SHAPE, "fact_head_rows: null buffer");
   FACT_REQUIRE(batch > 0 && d > 0 && d <= 8192 && out_dim > 0, FACT_ERR_BAD_SHAPE, "fact_head_rows: bad shape");
-  head_rows_kernel<<<batch, 1024, (d + 3 * 256) * sizeof(float), as_stream(stream)>>>(
-      x, row_stride, w_keras, bias, out, out_batch_stride, step_ptr, d, out_dim);
+  const dim3 grid(batch, (out_dim + HR_COLS - 1) / HR_COLS);
+  FACT_CUDA_CHECK(launch_k(head_rows_kernel, grid, dim3(256), (d + (HR_KG - 1) * HR_COLS) * sizeof(float),
+                           as_stream(stream), true, x, row_stride, w_keras, bias, out, out_batch_stride, step_ptr, d,
+                           out_dim));
   FACT_LAUNCH_CHECK("head_rows_kernel launch");
   return FACT_OK;
 }

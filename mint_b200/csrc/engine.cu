@@ -556,12 +556,12 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
                       static_cast<uintptr_t>(audio_len), static_cast<uintptr_t>(batch),
                       static_cast<uintptr_t>(hist_capacity), static_cast<uintptr_t>(mode)})
     key.add(x);
-  for (int f : {g_ar_prune, g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_dual_stream, g_gemm_tma_store, g_gemm_bn,
-                g_gemm_finish_ln, g_ar_fused})
-    key.add(static_cast<uintptr_t>(f));
   int device = 0;
   FACT_CUDA_CHECK(cudaGetDevice(&device));
   key.add(static_cast<uintptr_t>(device));
+  for (int f : {g_ar_prune, g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_dual_stream, g_gemm_tma_store, g_gemm_bn,
+                g_gemm_finish_ln, g_ar_fused, g_pdl})   // g_pdl stays LAST: the capture fallback below rewrites it
+    key.add(static_cast<uintptr_t>(f));
   ArSession* sess = session ? static_cast<ArSession*>(session) : &g_default_session;
   cudaGraphExec_t exec = nullptr;
   long long frame_kernels = 0;
@@ -576,21 +576,32 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
       }
   }
   if (!exec) {
-    cudaGraph_t graph = nullptr;
-    const long long before = g_launch_count;
-    FACT_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = one_frame(st);
-    frame_kernels = g_launch_count - before;
-    g_launch_count = before;  // captured, not executed: replays are counted below
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc) {
+    // Capture one frame.  With programmatic dependent launches the graph carries programmatic edges; should this
+    // driver refuse them at capture or instantiation, the frame is captured once more with plain launches (the flag is
+    // left off for the rest of the process and the key of this entry says so).
+    for (int attempt = 0; attempt < 2 && !exec; ++attempt) {
+      cudaGraph_t graph = nullptr;
+      const long long before = g_launch_count;
+      FACT_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = one_frame(st);
+      frame_kernels = g_launch_count - before;
+      g_launch_count = before;  // captured, not executed: replays are counted below
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc == FACT_OK && ce == cudaSuccess) {
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (ce != cudaSuccess) exec = nullptr;
+      }
       if (graph) cudaGraphDestroy(graph);
-      return rc;
+      if (exec) break;
+      if (attempt == 0 && g_pdl) {
+        cudaGetLastError();  // clear the sticky capture error
+        g_pdl = 0;
+        key.v.back() = 0;    // g_pdl is the last key word
+        continue;
+      }
+      if (rc) return rc;
+      return cuda_fail(ce, "AR frame graph capture / instantiate");
     }
-    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
-    ce = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
     std::lock_guard<std::mutex> lk(sess->mu);
     if (sess->entries.size() >= ArSession::kCapacity) {  // evict the least recently used entry only
       size_t victim = 0;

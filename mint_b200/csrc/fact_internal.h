@@ -44,4 +44,27 @@ int num_sms();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// fact_set_flag("pdl", 0 | 1): launch the small-batch decode chain (split-K GEMMs, finish kernels, attention core,
+// LayerNorm, embedding, head) as programmatic dependent launches -- every one of those kernels calls pdl_wait()
+extern int g_pdl;
+
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-dependent-launch attribute when `pdl` and g_pdl
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl && g_pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace fact

@@ -13,6 +13,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its stream predecessor is
+// still running: pdl_wait() blocks until the predecessor grid has COMPLETED and its memory is visible (a no-op for a
+// normal launch), pdl_trigger() lets the next kernel of the stream be scheduled early.  Rule used throughout: trigger
+// first thing, do the prologue that touches no global data (barrier init, TMEM alloc, descriptor prefetch, loads of
+// constant weights), then wait before the first read OR write of anything another kernel of the stream touches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_splitk_kernel(
   const int num_kb = (K + BK - 1) / BK;
   const int kb0 = z * kb_per, nkb = min(kb_per, num_kb - kb0);
   constexpr int TCOLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // one accumulator
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -433,18 +434,32 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_splitk_kernel(
     return smem_base + s * Cfg::STAGE_BYTES + NPART * A_TILE_BYTES + part_ * Cfg::B_TILE_BYTES;
   };
   if (warp == 0) {
+    // The W operand is constant (packed weights): the first ring fill of W goes out BEFORE the dependency wait, so
+    // under a programmatic dependent launch it streams from HBM while the previous kernel is still finishing; the
+    // activations (A) follow once that kernel has completed.
+    const int pre = nkb < STAGES ? nkb : STAGES;
+    if (elect_one()) {
+      for (int i = 0; i < pre; ++i) {
+        const int kc = (kb0 + i) * BK;
+        mbar_arrive_expect_tx(full_bar(i), Cfg::STAGE_BYTES);
+        tma_load_2d(sB(i, 0), &tmB0, kc, n0, full_bar(i));
+        if (NPART == 2) tma_load_2d(sB(i, 1), &tmB1, kc, n0, full_bar(i));
+      }
+    }
+    __syncwarp();
+    pdl_wait();
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
-      mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+      if (i >= pre) mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
       if (elect_one()) {
         const int kc = (kb0 + i) * BK;
-        mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-        tma_load_2d(sA(s, 0), &tmA0, kc, m0, full_bar(s));
-        tma_load_2d(sB(s, 0), &tmB0, kc, n0, full_bar(s));
-        if (NPART == 2) {
-          tma_load_2d(sA(s, 1), &tmA1, kc, m0, full_bar(s));
-          tma_load_2d(sB(s, 1), &tmB1, kc, n0, full_bar(s));
+        if (i >= pre) {
+          mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          tma_load_2d(sB(s, 0), &tmB0, kc, n0, full_bar(s));
+          if (NPART == 2) tma_load_2d(sB(s, 1), &tmB1, kc, n0, full_bar(s));
         }
+        tma_load_2d(sA(s, 0), &tmA0, kc, m0, full_bar(s));
+        if (NPART == 2) tma_load_2d(sA(s, 1), &tmA1, kc, m0, full_bar(s));
       }
       __syncwarp();
     }
@@ -473,6 +488,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_splitk_kernel(
     }
   } else {
     const int q = warp & 3;
+    pdl_wait();   // the slabs below may still be read by the finish kernel of the previous GEMM
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int row = m0 + q * 32 + lane;
@@ -507,6 +523,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_splitk_kernel(
 __global__ void __launch_bounds__(256) gemm_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
                                                           int kind, EpiArgs ep) {
   const long long total = static_cast<long long>(M) * N;
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
     const int row = static_cast<int>(i / N), col = static_cast<int>(i % N);
     float x = 0.f;
@@ -537,6 +555,8 @@ __global__ void __launch_bounds__(256) gemm_finish_vec_kernel(const float* __res
   const int nv = N >> 2;
   const long long total4 = static_cast<long long>(M) * nv;
   const long long slab4 = total4;  // float4 elements per split slab
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += 256ll * gridDim.x) {
     const int row = static_cast<int>(i / nv), col = static_cast<int>(i % nv) * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -588,6 +608,8 @@ __global__ void __launch_bounds__(256) gemm_finish_ln_kernel(const float* __rest
   const bool on = idx < nv;
   const size_t slab4 = static_cast<size_t>(M) * nv;
   float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_trigger();
+  pdl_wait();
   if (on) {
     const float4* p4 = reinterpret_cast<const float4*>(part) + static_cast<size_t>(row) * nv + idx;
     for (int zz = 0; zz < splits; ++zz) {
@@ -1164,21 +1186,25 @@ static int launch_splitk(const CUtensorMap& a0, const CUtensorMap& a1, const CUt
   }
   const int tiles_n = (n + BN - 1) / BN, tiles_m = (m + BM - 1) / BM;
   dim3 grid(tiles_n * tiles_m, splits);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, kb_per, part);
+  FACT_CUDA_CHECK(launch_k(kern, grid, dim3(192), Cfg::SMEM_BYTES, st, true, a0, a1, b0, b1, m, n, k, tiles_n, kb_per,
+                           part));
   FACT_LAUNCH_CHECK("gemm_tc_splitk_kernel launch");
   const long long total = static_cast<long long>(m) * n;
   if (ep.ln_hi != nullptr) {  // eligibility was checked by the caller (fact_gemm)
-    gemm_finish_ln_kernel<<<m, 256, 0, st>>>(part, splits, m, n, ep);
+    FACT_CUDA_CHECK(launch_k(gemm_finish_ln_kernel, dim3(m), dim3(256), 0, st, true, static_cast<const float*>(part),
+                             splits, m, n, ep));
     FACT_LAUNCH_CHECK("gemm_finish_ln_kernel launch");
     return FACT_OK;
   }
   if (ep.vec_ok && n % 4 == 0 && ep.ldo % 4 == 0) {  // vec_ok: pitches / pointers allow 16-byte accesses
     const long long total4 = total / 4;
     int fgrid = static_cast<int>((total4 + 255) / 256 > 2048 ? 2048 : (total4 + 255) / 256);
-    gemm_finish_vec_kernel<<<fgrid, 256, 0, st>>>(part, splits, m, n, kind, ep);
+    FACT_CUDA_CHECK(launch_k(gemm_finish_vec_kernel, dim3(fgrid), dim3(256), 0, st, true,
+                             static_cast<const float*>(part), splits, m, n, kind, ep));
   } else {
     int fgrid = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
-    gemm_finish_kernel<<<fgrid, 256, 0, st>>>(part, splits, m, n, kind, ep);
+    FACT_CUDA_CHECK(launch_k(gemm_finish_kernel, dim3(fgrid), dim3(256), 0, st, true, static_cast<const float*>(part),
+                             splits, m, n, kind, ep));
   }
   FACT_LAUNCH_CHECK("gemm_finish_kernel launch");
   return FACT_OK;
@@ -1268,6 +1294,7 @@ int g_gemm_tma_store = 1;  // fact_set_flag("gemm_tma_store", 0 | 1 | 2): pair-k
                            // (0 = direct row-per-lane stores, 2 = bulk stores but no in-place bulk reduction)
 int g_gemm_finish_ln = 1;  // fact_set_flag("gemm_finish_ln", 0): keep the LayerNorm out of the split-K finish kernel
                            // (batch 1: 722 frames/s fused, block per row, vs 656 with a separate LayerNorm launch)
+int g_pdl = 1;          // fact_set_flag("pdl", 0): plain serialized launches for the small-batch decode chain
 int g_gemm_pair = 1;    // fact_set_flag("gemm_pair", 0) forces the 1-SM kernel
 int g_gemm_splitk = 1;  // fact_set_flag("gemm_splitk", 0) disables the small-M split-K path
 
@@ -1374,7 +1401,7 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
     const int tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
     const int num_kb = (k + BK - 1) / BK;
     // only when the tiles alone fill less than ~1/3 of the SMs (else the extra finish launch costs more than it buys)
-    int splits = tiles <= 48 ? (num_sms() + tiles - 1) / tiles : 1;   // about one wave of CTAs
+    int splits = tiles <= 48 ? num_sms() / tiles : 1;   // at most ONE wave of CTAs (a 2nd wave doubles the kernel)
     if (splits > num_kb / 2) splits = num_kb / 2;          // at least 2 K blocks per CTA
     const size_t slab = static_cast<size_t>(m) * n * sizeof(float);
     if (splits > 1 && static_cast<size_t>(splits) * slab > epi->splitk_scratch_bytes)

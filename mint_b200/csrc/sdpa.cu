@@ -293,7 +293,7 @@ extern "C" int fact_set_flag(const char* name, int value) {
                         {"sdpa_bwd_tc", &g_sdpa_bwd_tc},   {"gemm_finish_ln", &g_gemm_finish_ln},
                         {"wgrad_pair", &g_wgrad_pair},     {"gemm_tma_store", &g_gemm_tma_store},
                         {"gemm_splitk", &g_gemm_splitk},   {"gemm_pair", &g_gemm_pair},
-                        {"ar_fused", &g_ar_fused}};
+                        {"ar_fused", &g_ar_fused},         {"pdl", &g_pdl}};
   for (const Flag& f : flags)
     if (name && strcmp(name, f.name) == 0) {
       *f.slot = value;

@@ -87,11 +87,13 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     mbar_init(o_empty, TC_SM_WARPS);
     fence_barrier_init();
   }
+  pdl_trigger();
   if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr_addr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();   // q / k / v come from the QKV GEMM before this launch; o_hi / o_lo may still be read by the one before
 
   auto tile_coords = [&](int tile, int& b, int& h, int& qb) {
     qb = tile % q_blocks;
@@ -332,7 +334,8 @@ static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, fl
   const int q_blocks = (q_rows + TC_QB - 1) / TC_QB;
   const int num_tiles = q_blocks * heads * batch;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmh, tml, oh, ol, lse, n, heads, q_blocks, num_tiles);
+  FACT_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, true, tmh, tml, oh, ol, lse, n, heads,
+                           q_blocks, num_tiles));
   FACT_LAUNCH_CHECK("sdpa_tc_kernel launch");
   return FACT_OK;
 }

