@@ -1,6 +1,13 @@
 // Weight-gradient GEMM on CTA pairs: dW[in, out] += X^T . dY over the tokens (reference semantics: tape.gradient of the
 // Dense kernels, mint/ctl/single_task_trainer.py:176-178).
 //
+// Tile = 256 (M side, fixed by cta_group::2) x NT (N side, any multiple of 16 up to 256).  FACT's Dense kernels are
+// 800 wide on one side (d_model) and 800 / 2400 / 3072 on the other, and 800 = 3.125 x 256: with square 256-tiles a
+// fifth of the MMAs multiplied zero padding.  So the N side is cut into EQUAL tiles just wide enough (800 -> 4 x 208,
+// 2400 -> 10 x 240, 3072 -> 12 x 256), and when it is the `in` dimension that is 800 wide the product is computed
+// transposed (M side = out, N side = in; the epilogue transposes its 32 x 32 boxes on the way to shared memory).
+// Executed MMA work per layer drops by 19 % (dW1, dW2: 1.28 -> 1.04 x the useful flops; dWqkv 1.37 -> 1.11).
+//
 // The 1-SM kernel in backward.cu (128 x 128 tiles) needs 128 bytes of operands per MMA clock and is bound by the
 // L2 -> SM path at a third of the tensor peak.  Here a cluster of two CTAs owns a 256 x 256 tile (cta_group::2: each CTA
 // stages its own 128 `in` rows of X^T and 128 of the 256 `out` columns of dY), which halves the operand bytes per flop:
@@ -22,12 +29,14 @@ constexpr int W2_STAGING_BYTES = W2_EPI_WARPS * 4096;
 constexpr int W2_SMEM_BYTES = 1024 + W2_STAGES * W2_STAGE_BYTES + W2_STAGING_BYTES + 256;
 static_assert(W2_SMEM_BYTES <= 232448, "exceeds 227 KB");
 
-// tmX: {in (inner), tokens}, tmY: {out (inner), tokens}, tmW: fp32 dW {out (inner), in}, box 32 x 32 SWIZZLE_128B.
 // Work item w -> (tile = w / splits, slice = w % splits); slice z covers token blocks [z * kb_per, (z + 1) * kb_per).
+// tmX: A operand {M-side dim (inner), tokens}, tmY: B operand {N-side dim (inner), tokens} (X and dY, or dY and X when
+// `swapped`), tmW: fp32 dW {out (inner), in}, box 32 x 32 SWIZZLE_128B.  MDIM / NDIM: extents of the M / N side; NT: N
+// tile width (multiple of 16, <= 256; each CTA stages NT / 2 columns of the B operand).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_wgrad2_kernel(
     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-    const __grid_constant__ CUtensorMap tmW, int IN, int OUT, int tiles_out, int num_items, int splits, int num_kb,
-    int kb_per) {
+    const __grid_constant__ CUtensorMap tmW, int MDIM, int NDIM, int NT, int swapped, int tiles_out, int num_items,
+    int splits, int num_kb, int kb_per) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -79,8 +88,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
     uint32_t it = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int tile = item / splits;
-      const int m0 = (tile / tiles_out) * 256 + rank * 128;  // this CTA's `in` rows
-      const int n0 = (tile % tiles_out) * 256 + rank * 128;  // this CTA's half of the `out` columns
+      const int m0 = (tile / tiles_out) * 256 + rank * 128;       // this CTA's rows of the M side
+      const int n0 = (tile % tiles_out) * NT + rank * (NT >> 1);  // this CTA's half of the tile's N-side columns
       int kb0;
       const int nkb = item_kb(item, kb0);
       for (int i = 0; i < nkb; ++i, ++it) {
@@ -100,7 +109,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
     }
   } else if (warp == 1) {
     if (leader) {  // ---------------- MMA issuer
-      constexpr uint32_t idesc = umma_idesc_bf16_f32_maj(256, 256, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16_f32_maj(256, NT, 1, 1);
       uint32_t it = 0, t = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++t) {
         const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
@@ -129,35 +138,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
       }
     }
   } else {
-    // ---------------- epilogue warps (both CTAs): this CTA's 128 `in` rows x 256 `out` columns
+    // ---------------- epilogue warps (both CTAs): this CTA's 128 M-side rows x NT N-side columns
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t stg = staging_base + static_cast<uint32_t>(warp - 2) * 4096;
     uint32_t t = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++t) {
       const int tile = item / splits;
       const int row0 = (tile / tiles_out) * 256 + rank * 128 + q * 32;
-      const int n0 = (tile % tiles_out) * 256;
+      const int n0 = (tile % tiles_out) * NT;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
 #pragma unroll 1
       for (int c = half; c < 8; c += 2) {
         const int col0 = n0 + c * 32;
-        if (col0 >= OUT || row0 >= IN) continue;
+        const int valid = NT - c * 32;  // tile columns of this 32-wide chunk the MMA wrote (the rest is stale TMEM)
+        if (valid <= 0 || col0 >= NDIM || row0 >= MDIM) continue;
         float v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + c * 32, v);
         tmem_ld_wait();
+        if (valid < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= valid) v[i] = 0.f;  // these columns belong to the next tile: add zero there
+        }
         if (lane == 0) bulk_wait_group_read0();
         __syncwarp();
-        const uint32_t rbase = stg + lane * 128, sw = lane & 7;
+        if (!swapped) {
+          // box[row = lane (in)][col = i (out)]: 16-byte chunks, swizzled like the tensor map expects
+          const uint32_t rbase = stg + lane * 128, sw = lane & 7;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          st_shared_v4(rbase + ((i ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
-                       __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(rbase + ((i ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                         __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+        } else {
+          // transposed: this lane holds out = row0 + lane, in = col0 + i -> box[row = i (in)][col = lane (out)].
+          // For a fixed i the 32 lanes write 32 distinct words of one 128-byte row: conflict-free scalar stores.
+          const uint32_t cchunk = static_cast<uint32_t>(lane) >> 2, cword = (static_cast<uint32_t>(lane) & 3) << 2;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t addr = stg + i * 128 + ((cchunk ^ (i & 7)) << 4) + cword;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v[i]) : "memory");
+          }
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_reduce_add_2d(&tmW, stg, col0, row0);
+          if (!swapped) tma_reduce_add_2d(&tmW, stg, col0, row0);   // {out, in} = {N side, M side}
+          else tma_reduce_add_2d(&tmW, stg, row0, col0);            // {out, in} = {M side, N side}
           bulk_commit_group();
         }
       }
@@ -180,7 +208,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
   }
 }
 
-int g_wgrad_pair = 1;  // fact_set_flag("wgrad_pair", 0): keep the 1-SM 128 x 128 kernel (A/B timing, tests)
+// fact_set_flag("wgrad_pair", v): 0 keeps the 1-SM 128 x 128 kernel (A/B timing, tests), 1 = pair kernel with the cheaper
+// orientation, 2 / 3 force the plain / transposed orientation (tests)
+int g_wgrad_pair = 1;
 
 // returns FACT_OK and sets *done when the pair kernel took the problem; *done = false -> caller uses the 1-SM kernel
 int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dW, int ldw, int tokens, int in_dim,
@@ -195,13 +225,23 @@ int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, f
     FACT_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BYTES));
     attr_done = true;
   }
+  // Orientation: the M side is cut into 256-row tiles, the N side into equal tiles of up to 256 columns; pick the
+  // orientation (and with it the padding) that executes fewer MMA columns.  swapped = M side is `out`.
+  auto pad_m = [](int v) { return (v + 255) / 256 * 256; };
+  auto tiles_n_of = [](int v) { return (v + 255) / 256; };
+  auto nt_of = [&](int v) { return ((v + tiles_n_of(v) - 1) / tiles_n_of(v) + 15) / 16 * 16; };
+  const long long cost_plain = static_cast<long long>(pad_m(in_dim)) * tiles_n_of(out_dim) * nt_of(out_dim);
+  const long long cost_swap = static_cast<long long>(pad_m(out_dim)) * tiles_n_of(in_dim) * nt_of(in_dim);
+  const int swapped = (g_wgrad_pair != 2 && cost_swap < cost_plain) || g_wgrad_pair == 3 ? 1 : 0;
+  const int m_dim = swapped ? out_dim : in_dim, n_dim = swapped ? in_dim : out_dim;
+  const int nt = nt_of(n_dim);
   CUtensorMap tmx, tmy, tmw;
   int rc;
   if ((rc = make_tmap_bf16(&tmx, x_bf16, tokens, in_dim, ldx, 64, 64))) return rc;
   if ((rc = make_tmap_bf16(&tmy, dy_bf16, tokens, out_dim, ldy, 64, 64))) return rc;
   if ((rc = make_tmap_out(&tmw, dW, in_dim, out_dim, ldw, 4))) return rc;
-  const int tiles_in = (in_dim + 255) / 256, tiles_out = (out_dim + 255) / 256;
-  const int tiles = tiles_in * tiles_out;
+  const int tiles_m = (m_dim + 255) / 256, tiles_out = tiles_n_of(n_dim);
+  const int tiles = tiles_m * tiles_out;
   const int num_kb = (tokens + W2_BK - 1) / W2_BK;
   const int clusters_max = num_sms() / 2;
   // token slices: the split that fills whole rounds of the persistent clusters best, with >= 24 token blocks per item
@@ -223,8 +263,9 @@ int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, f
   const int splits = (num_kb + kb_per - 1) / kb_per;
   const int num_items = tiles * splits;
   const int clusters = num_items < clusters_max ? num_items : clusters_max;
-  gemm_wgrad2_kernel<<<2 * clusters, W2_THREADS, W2_SMEM_BYTES, st>>>(tmx, tmy, tmw, in_dim, out_dim, tiles_out,
-                                                                      num_items, splits, num_kb, kb_per);
+  gemm_wgrad2_kernel<<<2 * clusters, W2_THREADS, W2_SMEM_BYTES, st>>>(swapped ? tmy : tmx, swapped ? tmx : tmy, tmw, m_dim,
+                                                                      n_dim, nt, swapped, tiles_out, num_items, splits,
+                                                                      num_kb, kb_per);
   FACT_LAUNCH_CHECK("gemm_wgrad2_kernel launch");
   *done = true;
   return FACT_OK;

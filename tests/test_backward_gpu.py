@@ -32,15 +32,17 @@ def test_wgrad_gemm(fact_lib, cuda, tokens, in_dim, out_dim):
 @pytest.mark.parametrize("tokens,in_dim,out_dim", [(4608, 800, 2400), (5000, 3072, 800), (4100, 304, 520),
                                                     (4096, 256, 256), (9001, 800, 3072), (12000, 800, 800)])
 def test_wgrad_gemm_pair(fact_lib, cuda, tokens, in_dim, out_dim):
-    """Problems large enough for the CTA-pair kernel (256 x 256 tiles, bulk fp32 reductions into dW): partial tiles on
-    both matrix edges, a token count that is not a multiple of the 64-token block, accumulation on top of dW, nothing
-    written outside [in, out]; and the 1-SM kernel (flag off) agrees."""
+    """Problems large enough for the CTA-pair kernel (256 x NT tiles, bulk fp32 reductions into dW): partial tiles on
+    both matrix edges, N tiles that are not a multiple of the 32-column epilogue chunk (800 -> 4 x 208, 520 -> 3 x 176),
+    a token count that is not a multiple of the 64-token block, accumulation on top of dW, nothing written outside
+    [in, out]; the automatic orientation (flag 1), the plain (2) and the transposed (3) one and the 1-SM kernel (0)
+    agree."""
     g = torch.Generator(device="cpu").manual_seed(1)
     x = torch.randn(tokens, in_dim, generator=g).to(cuda).to(BF)
     dy = torch.randn(tokens, out_dim, generator=g).to(cuda).to(BF)
     ref = x.double().t() @ dy.double() + 0.5
     outs = []
-    for flag in (1, 0):
+    for flag in (1, 2, 3, 0):
         fact_lib.fact_set_flag(b"wgrad_pair", flag)
         buf = torch.full((in_dim + 8, out_dim), 0.5, device=cuda)     # 8 guard rows behind the gradient
         try:
@@ -52,7 +54,8 @@ def test_wgrad_gemm_pair(fact_lib, cuda, tokens, in_dim, out_dim):
         assert (buf[in_dim:] == 0.5).all(), f"flag {flag}: wrote past row {in_dim}"
         assert rel_err(buf[:in_dim], ref) < 2e-5, (flag, rel_err(buf[:in_dim], ref))
         outs.append(buf[:in_dim].clone())
-    assert rel_err(outs[0], outs[1].double()) < 1e-5
+    for o in outs[1:]:
+        assert rel_err(outs[0], o.double()) < 1e-5
 
 
 def test_wgrad_gemm_padded_operand(fact_lib, cuda):
