@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libfact_sm100.so")
-SOURCES = ["elementwise.cu", "gemm_tc.cu", "sdpa.cu", "sdpa_tc.cu", "engine.cu", "backward.cu", "wgrad_tc.cu", "sdpa_bwd_tc.cu", "engine_train.cu"]
+SOURCES = ["elementwise.cu", "gemm_tc.cu", "sdpa.cu", "sdpa_tc.cu", "engine.cu", "backward.cu", "wgrad_tc.cu", "sdpa_bwd_tc.cu", "sdpa_bwd_tc2.cu", "engine_train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

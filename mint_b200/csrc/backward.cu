@@ -717,6 +717,9 @@ int wgrad_gemm(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float*
 
 int sdpa_bwd_tc_try(const bf16* qkv, const bf16* d_o, const float* lse, const float* Dv, bf16* dqkv, float* dq_acc,
                     int batch, int n, int heads, int head_dim, float k_scale, cudaStream_t st, bool* done);  // sdpa_bwd_tc.cu
+int sdpa_bwd_tc2_try(const bf16* qkv, const bf16* d_o, const float* lse, const float* Dv, bf16* dqkv, float* dq_acc,
+                     int batch, int n, int heads, int head_dim, float k_scale, cudaStream_t st, bool* done);  // sdpa_bwd_tc2.cu
+extern int g_sdpa_bwd_tc;
 
 int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* lse, float* Dv, float* dq_acc,
                   void* dqkv, int batch, int n, int heads, int head_dim, float scale, cudaStream_t st) {
@@ -734,8 +737,13 @@ int sdpa_backward(const void* qkv, const void* o, const void* d_o, const float* 
   }
   dim3 grid((n + 63) / 64, heads, batch);
   const float k_scale = 0.6931471805599453f;  // dK = ln2 * dZ^T q'   (q' = q * scale * log2 e)
-  bool tc_done = false;  // FACT shapes: the tcgen05 kernel
-  {
+  bool tc_done = false;  // FACT shapes: the tcgen05 kernels (flag sdpa_bwd_tc: 1 = pipelined, 2 = first generation)
+  if (g_sdpa_bwd_tc == 1) {
+    const int rc = sdpa_bwd_tc2_try(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_o), lse, Dv,
+                                    static_cast<bf16*>(dqkv), dq_acc, batch, n, heads, head_dim, k_scale, st, &tc_done);
+    if (rc != FACT_OK) return rc;
+  }
+  if (!tc_done) {
     const int rc = sdpa_bwd_tc_try(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_o), lse, Dv,
                                    static_cast<bf16*>(dqkv), dq_acc, batch, n, heads, head_dim, k_scale, st, &tc_done);
     if (rc != FACT_OK) return rc;

@@ -96,7 +96,8 @@ def test_gelu_save_and_grad_epilogues(fact_lib, cuda):
 
 @pytest.mark.parametrize("legacy", [0, 1])
 @pytest.mark.parametrize("batch,n,heads,dh", [(2, 120, 10, 80), (1, 360, 10, 80), (2, 37, 2, 16), (1, 130, 3, 64),
-                                              (3, 240, 4, 80), (3, 360, 10, 80), (5, 200, 2, 80), (2, 384, 1, 80)])
+                                              (3, 240, 4, 80), (3, 360, 10, 80), (5, 200, 2, 80), (2, 384, 1, 80),
+                                              (40, 360, 10, 80), (2, 68, 3, 80), (3, 130, 2, 80)])
 def test_sdpa_forward_lse_and_backward(fact_lib, cuda, batch, n, heads, dh, legacy):
     if legacy and dh != 80:
         pytest.skip("already the mma.sync path")
@@ -131,7 +132,8 @@ def test_sdpa_forward_lse_and_backward(fact_lib, cuda, batch, n, heads, dh, lega
     d_o = torch.randn(batch * n, d, generator=g).to(cuda).to(BF)
     out.backward(d_o.double())
     dref = torch.stack([t.grad.permute(0, 2, 1, 3).reshape(batch * n, d) for t in (q, k, v)], 1).reshape(batch * n, 3 * d)
-    for bwd_tc in ((1, 0) if dh == 80 else (1,)):              # tcgen05 kernel, then the mma.sync kernel
+    # pipelined tcgen05 kernel (1: 64-query steps, two score buffers), first-generation tcgen05 kernel (2), mma.sync (0)
+    for bwd_tc in ((1, 2, 0) if dh == 80 else (1,)):
         dqkv = torch.zeros(batch * n, 3 * d, device=cuda, dtype=BF)
         dscr = torch.zeros(batch * heads * n, device=cuda)
         dq_scr = torch.zeros(batch * n * d, device=cuda)
