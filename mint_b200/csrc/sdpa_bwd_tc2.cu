@@ -8,9 +8,11 @@
 // 64 queries, which halves the score columns and lets TWO score buffers live in TMEM next to the accumulators:
 //   TMEM columns: buffer b: S^T / P^T [128 b, 128 b + 64)  dP^T / dZ^T [128 b + 64, 128 b + 128)   (b = 0, 1)
 //                 dV [256, 336)   dK [336, 416)   dQ [416, 496)
-// so the issuer runs the score MMAs of step i + 1 while the softmax warps turn step i into P^T / dZ^T, and the softmax
-// warps read dQ of step i - 1 out of TMEM while the dV / dK / dQ MMAs of step i run: neither side waits for the other
-// in steady state.
+// so the issuer runs the score MMAs of step i + 1 while the softmax warps turn step i into P^T / dZ^T, and two
+// dedicated warps drain dQ of step i out of TMEM (-> shared memory -> bulk reduction) while the softmax warps are
+// already on step i + 1: in steady state no role waits for another.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax (TMEM lane quadrant = warp % 4, two warps per quadrant
+// split the 64 query columns), 12 / 13 = dQ read-out (quadrants 0 / 1 = the 64 query lanes), 10 / 11 idle.
 //
 //   work item = (batch, head, 128-key block j); for every 64-query block i:
 //     S^T  = K_j . Q_i^T   [128 keys x 64 queries]     dP^T = V_j . dO_i^T
@@ -37,7 +39,8 @@ constexpr int B2_OPQ = B2_KS * B2_SUBQ;       // 10 KB: Q_i or dO_i
 constexpr int B2_QSTAGES = 4;
 constexpr int B2_STAGE = 21 * 1024;           // Q_i | dO_i | lse[64] | D[64] (+ pad to a 1024-byte multiple)
 constexpr int B2_SM_WARPS = 8;
-constexpr int B2_THREADS = 64 + B2_SM_WARPS * 32;
+constexpr int B2_RO_WARP0 = 12;                // read-out warps 12 / 13 own TMEM lane quadrants 0 / 1 (warp % 4)
+constexpr int B2_THREADS = 14 * 32;
 constexpr int B2_COL_DV = 256, B2_COL_DK = 336, B2_COL_DQ = 416;
 
 constexpr int B2_OFF_K = 0;
@@ -93,7 +96,7 @@ sdpa_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
       mbar_init(p_ready(b), B2_SM_WARPS);
     }
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);  // the four warps that own TMEM lanes 0..63 (the 64 queries of a step)
+    mbar_init(dq_empty, 2);  // the two read-out warps (TMEM lanes 0..63 = the 64 queries of a step)
     mbar_init(dkv_full, 1);
     mbar_init(dkv_empty, B2_SM_WARPS);
     fence_barrier_init();
@@ -223,40 +226,38 @@ sdpa_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         __syncwarp();
       }
     }
-  } else {
-    // ------------------------------------------------------------------ softmax / epilogue warps 2..9
-    const int q4 = warp & 3, half = (warp - 2) >> 2;
+  } else if (warp >= B2_RO_WARP0) {
+    // ------------------------------------------------------------------ dQ read-out warps 12, 13
+    // dQ_i [64 queries x 80] sits in TMEM lanes 0..63: warp 12 owns lanes 0..31, warp 13 lanes 32..63 (a warp reaches
+    // the lane quadrant warp % 4).  Each step: TMEM -> registers -> five swizzled [32 rows][16 col] fp32 boxes in shared
+    // memory -> bulk tensor reduction into dq_acc; the softmax warps never wait for any of it.
+    const int q4 = warp & 3;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-    const int rl = q4 * 32 + lane;  // row (TMEM lane) inside the block: a key for S^T / dP^T / dV / dK, a query for dQ
-    const uint32_t dq_stage = smem_base + B2_OFF_DQ + static_cast<uint32_t>(warp - 2) * 3 * 2048;
-    uint32_t it = 0, t = 0;
-
-    // dQ partial of global step g (queries q0 .. q0 + 63 of clip row base tok0): TMEM lanes 0..63 only
-    auto readout_dq = [&](uint32_t g, int q0, size_t tok0, int h) {
-      if (q4 >= 2) return;
-      constexpr int C0 = 48;  // half 0 takes columns [0, 48), half 1 [48, 80)
-      mbar_wait(dq_full, g & 1);
-      tc_fence_after();
-      float dq[C0];
-      if (half == 0) {
+    const uint32_t dq_stage = smem_base + B2_OFF_DQ + static_cast<uint32_t>(warp - B2_RO_WARP0) * B2_KS * 2048;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int b, h, jb;
+      item_coords(item, b, h, jb);
+      const size_t tok0 = static_cast<size_t>(b) * N;
+      for (int ib = 0; ib < nqb; ++ib, ++g) {
+        const int q0 = ib * B2_QB;
+        mbar_wait(dq_full, g & 1);
+        tc_fence_after();
+        float dq[B2_DH];
         tmem_ld_32x32(lane_base + B2_COL_DQ, dq);
-        tmem_ld_32x16(lane_base + B2_COL_DQ + 32, dq + 32);
-      } else {
-        tmem_ld_32x32(lane_base + B2_COL_DQ + C0, dq);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(dq_empty);
-        bulk_wait_group_read0();  // the previous step's boxes have left this warp's staging slot
-      }
-      __syncwarp();
-      const int nsub = half == 0 ? 3 : 2;
-      const uint32_t sw = (lane >> 1) & 3;
+        tmem_ld_32x32(lane_base + B2_COL_DQ + 32, dq + 32);
+        tmem_ld_32x16(lane_base + B2_COL_DQ + 64, dq + 64);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(dq_empty);
+          bulk_wait_group_read0();  // the previous step's boxes have left the staging slot
+        }
+        __syncwarp();
+        const uint32_t sw = (lane >> 1) & 3;
 #pragma unroll
-      for (int sb = 0; sb < 3; ++sb)
-        if (sb < nsub) {
+        for (int sb = 0; sb < B2_KS; ++sb) {
           const uint32_t rb = dq_stage + sb * 2048 + lane * 64;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
@@ -264,15 +265,23 @@ sdpa_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
                          __float_as_uint(dq[sb * 16 + 4 * c4 + 1]), __float_as_uint(dq[sb * 16 + 4 * c4 + 2]),
                          __float_as_uint(dq[sb * 16 + 4 * c4 + 3]));
         }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && q0 + q4 * 32 < N) {  // rows past N hold exact zeros: skip wholly empty boxes
-        const int col = h * B2_DH + (half == 0 ? 0 : C0);
-        const int row = static_cast<int>(tok0) + q0 + q4 * 32;
-        for (int sb = 0; sb < nsub; ++sb) tma_reduce_add_2d(&tm_dq, dq_stage + sb * 2048, col + sb * 16, row);
-        bulk_commit_group();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && q0 + q4 * 32 < N) {  // rows past N hold exact zeros: skip wholly empty boxes
+          const int row = static_cast<int>(tok0) + q0 + q4 * 32;
+#pragma unroll
+          for (int sb = 0; sb < B2_KS; ++sb) tma_reduce_add_2d(&tm_dq, dq_stage + sb * 2048, h * B2_DH + sb * 16, row);
+          bulk_commit_group();
+        }
       }
-    };
+    }
+    if (lane == 0) bulk_wait_group0();
+  } else if (warp >= 2 && warp < 2 + B2_SM_WARPS) {
+    // ------------------------------------------------------------------ softmax / epilogue warps 2..9
+    const int q4 = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    const int rl = q4 * 32 + lane;  // row (TMEM lane) inside the block: a key for S^T / dP^T / dV / dK, a query for dQ
+    uint32_t it = 0, t = 0;
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
       int b, h, jb;
@@ -326,10 +335,7 @@ sdpa_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready(buf));
-        // while the dV / dK / dQ MMAs of this step run: read the PREVIOUS step's dQ out of TMEM
-        if (ib > 0) readout_dq(it - 1, i0 - B2_QB, tok0, h);
       }
-      readout_dq(it - 1, (nqb - 1) * B2_QB, tok0, h);
       // ---- dV_j (half 0) / dK_j (half 1): TMEM lane = key
       mbar_wait(dkv_full, t & 1);
       tc_fence_after();
@@ -355,7 +361,6 @@ sdpa_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         }
       }
     }
-    if (lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before();
