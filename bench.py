@@ -367,9 +367,10 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
                       "global_batch": B * world, "products": "bf16 (fp32 accumulate, fp32 master weights / Adam state)",
                       "loss": "L2 motion loss on the first 20 frames", "optimizer": "Keras Adam",
                       "parallelism": f"dp{world}: one logical all-reduce of the flat fp32 gradient bucket per step, "
-                                     "issued as contiguous slices in the order the backward finishes them (see "
-                                     "allreduce_slices_mb); all but the last overlap the rest of the backward on a side "
-                                     "stream" if world > 1 else "single GPU"}}
+                                     "issued as contiguous slices (allreduce_slices_mb) and hidden as allreduce_overlap "
+                                     "says: 'adam' = the Adam update of a slice runs while the next slice is on the "
+                                     "wire; 'backward' = slices follow the backward's stage events on a side stream"
+                                     if world > 1 else "single GPU"}}
     with torch.cuda.stream(stream):
         batch_d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         dp = SingleTaskTrainer([], "target", model, optimizer=opt)
@@ -445,7 +446,9 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
         "frac_of_sustained_tensor_peak": TRAIN_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
         "allreduce_ms": ar_ms, "exposed_allreduce_ms": exposed, "ms_per_step_without_allreduce": ms_local,
         "grad_bucket_mb": model.flat_gradients.numel() * 4 / 1e6,
-        "allreduce_slices_mb": [round(c * 4 / 1e6, 1) for _, c, _ in dp._plan] if world > 1 and dp._plan else None,
+        "allreduce_overlap": dp.overlap if world > 1 else None,
+        "allreduce_slices_mb": ([round(c * 4 / 1e6, 1) for _, c, _ in dp._plan] if dp._plan else
+                                [round(c * 4 / 1e6, 1) for _, c in dp.even_slices()]) if world > 1 else None,
         "allreduce_busbw_gbs": (model.flat_gradients.numel() * 4 * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9
                                 if ar_ms else None),
         "gpu_topology": gpu_topology(world) if rank == 0 else None,

@@ -256,10 +256,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(
     }
     fence_barrier_init();
   }
+  pdl_trigger();
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_addr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   auto sA = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + part * A_TILE_BYTES; };
@@ -836,12 +838,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     }
     fence_barrier_init();
   }
+  pdl_trigger();
   if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr_addr);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();  // programmatic dependent launch: everything above overlapped the previous kernel's tail
 
   auto sA = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + part * A_TILE_BYTES; };
   auto sB = [&](int s, int part) {
@@ -1168,7 +1172,8 @@ static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   const int tiles_n = (n + BN - 1) / BN, tiles_m = (m + BM - 1) / BM;
   const int num_tiles = tiles_n * tiles_m;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, m, n, k, tiles_n, num_tiles, ep);
+  FACT_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, true, a0, a1, b0, b1, m, n, k,
+                           tiles_n, num_tiles, ep));
   FACT_LAUNCH_CHECK("gemm_tc_kernel launch");
   return FACT_OK;
 }
@@ -1228,8 +1233,8 @@ static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   const int num_tiles = tiles_n * tiles_m;
   int clusters = num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b0, b1, om.o0, om.o1, m, n, k, tiles_n, num_tiles,
-                                                            ep);
+  FACT_CUDA_CHECK(launch_k(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, true, a0, a1, b0, b1, om.o0,
+                           om.o1, m, n, k, tiles_n, num_tiles, ep));
   FACT_LAUNCH_CHECK("gemm_tc2_kernel launch");
   return FACT_OK;
 }

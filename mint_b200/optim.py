@@ -74,18 +74,33 @@ class Adam:
 
     def apply_gradients(self, grad_scale: float = 1.0) -> None:
         """w -= lr_t * m / (sqrt(v) + eps) on the whole bucket, then refresh the bf16 operand copies."""
+        self.begin_step()
+        self.apply_range(0, self.model.flat_parameters.numel(), grad_scale)
+        self.end_step()
+
+    # The same update in pieces: begin_step(), apply_range() over disjoint slices that together cover the bucket (any
+    # order), end_step().  The data-parallel trainer updates a slice as soon as its all-reduce has landed, while the
+    # next slice is still on the wire.
+    def begin_step(self) -> None:
+        self._lr = self.current_lr()
+        self.iterations += 1
+
+    def apply_range(self, offset: int, count: int, grad_scale: float = 1.0) -> None:
         model = self.model
         flat, grad = model.flat_parameters, model.flat_gradients
-        lr = self.current_lr()
-        self.iterations += 1
+        if offset % 4 or offset < 0 or offset + count > flat.numel():
+            raise ValueError("slice must start on a 16-byte boundary inside the bucket")
         with torch.cuda.device(model.device):
             st = torch.cuda.current_stream(model.device).cuda_stream
             kl = model.flat_bf16_parameters      # bf16 copy of the bucket (Keras-layout operands of the dX GEMMs)
-            lib.check(self._lib.fact_adam_step(flat.data_ptr(), grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                               flat.numel(), lr, self.beta_1, self.beta_2, self.epsilon,
-                                               self.iterations, float(grad_scale),
-                                               kl.data_ptr() if kl is not None else None, st), "fact_adam_step")
-        model.repack(bf16_copy_done=kl is not None)
+            lib.check(self._lib.fact_adam_step(
+                flat.data_ptr() + 4 * offset, grad.data_ptr() + 4 * offset, self.m.data_ptr() + 4 * offset,
+                self.v.data_ptr() + 4 * offset, count, self._lr, self.beta_1, self.beta_2, self.epsilon,
+                self.iterations, float(grad_scale), kl.data_ptr() + 2 * offset if kl is not None else None, st),
+                "fact_adam_step")
+
+    def end_step(self) -> None:
+        self.model.repack(bf16_copy_done=self.model.flat_bf16_parameters is not None)
 
     def state_dict(self):
         return {"iterations": self.iterations, "m": self.m, "v": self.v}

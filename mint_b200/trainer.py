@@ -4,13 +4,22 @@ Same step semantics: pop the label, forward, `loss / num_replicas`, gradients, o
 clip_by_global_norm BEFORE the cross-replica sum (single_task_trainer.py:180-183), one SUM all-reduce of all gradients
 (what MirroredStrategy does inside apply_gradients, :186-187), Adam.  One process per GPU.
 
-The cross-replica sum is ONE logical all-reduce of the model's flat gradient bucket, issued as a few contiguous slices
-in the order the backward pass finishes them (FACTModel.gradient_stages: head, cross layers top to bottom, motion
-encoder, audio encoder; adjacent layers are merged into `allreduce_chunks` slices of similar size).  All but the last
-run on a side stream behind the events fact_train_step records, so they overlap the rest of the backward; only the
-last slice (the bottom layer of the audio encoder + its embeddings, 6 % of the bucket) is exposed.  Clipping needs the
-norm of the whole gradient before any slice may be summed, so with grad_clip_norm > 0 the reduce is a single call after
-the backward; the clip factor is computed and applied on the device (no host synchronisation).
+The cross-replica sum is ONE logical all-reduce of the model's flat gradient bucket, issued as a few contiguous slices.
+Two ways to hide it, chosen by `overlap` ("auto" times one all-reduce of the bucket at construction):
+
+  "adam"      (fast links: NVLink / NVSwitch, the all-reduce is about as long as the optimizer pass).  All slices are
+              issued right after the backward; the Adam update of slice i runs as soon as slice i has landed, while
+              slice i + 1 is on the wire, so the update hides most of the transfer.  Measured on 8 x B200 (NV18): the
+              all-reduce alone takes 1.4 ms; overlapping it with the BACKWARD instead made the step 2.1 ms longer,
+              because every GEMM of the backward is a persistent one-CTA-per-SM kernel with a static tile map and the
+              NCCL kernel takes SMs away from it (the displaced CTAs run as a second wave).
+  "backward"  (slow links: the all-reduce is several times the optimizer pass).  Slices are reduced on a side stream in
+              the order the backward finishes them (FACTModel.gradient_stages: head, cross layers top to bottom, motion
+              encoder, audio encoder) behind the events fact_train_step records; only the last slice is exposed.
+              Measured on a 2-GPU box whose pair ran at 75 GB/s: 6.4 ms all-reduce, 2.8 ms exposed.
+
+Clipping needs the norm of the whole gradient before any slice may be summed, so with grad_clip_norm > 0 the
+"backward" mode is not available; the clip factor is computed and applied on the device (no host synchronisation).
 """
 from __future__ import annotations
 
@@ -22,9 +31,10 @@ import torch.distributed as dist
 
 class SingleTaskTrainer:
     def __init__(self, train_dataset, label_key, model, loss_fn=None, optimizer=None, metrics=None,
-                 trainer_options=None, summary_fn=None, grad_clip_norm: float = 0.0, overlap_allreduce: bool = True,
+                 trainer_options=None, summary_fn=None, grad_clip_norm: float = 0.0, overlap: str = "auto",
                  allreduce: bool = True, allreduce_chunks: int = 8):
         """train_dataset: iterable of dict batches (torch / numpy); label_key: 'target' (trainer.py:157).
+        overlap: "auto" | "adam" | "backward" | "none" (see the module docstring).
         allreduce=False skips the cross-replica sum (bench.py uses it to measure how much of it is exposed)."""
         self.train_dataset = train_dataset
         self.label_key = label_key
@@ -37,13 +47,30 @@ class SingleTaskTrainer:
         self._iter = None
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.allreduce = allreduce
-        self.overlap = bool(overlap_allreduce) and hasattr(model, "gradient_stages")
+        self.chunks = max(1, int(allreduce_chunks))
+        if overlap not in ("auto", "adam", "backward", "none"):
+            raise ValueError("overlap must be auto, adam, backward or none")
+        staged_ok = hasattr(model, "gradient_stages")
+        sliced_ok = hasattr(optimizer, "apply_range")
+        self.calibration_ms = None
+        if overlap == "auto":
+            overlap = "adam" if sliced_ok else ("backward" if staged_ok else "none")
+            if self.world > 1 and allreduce and staged_ok and sliced_ok:
+                self.calibration_ms = self._time_allreduce()
+                # the optimizer pass over the bucket is ~1 ms; a transfer several times that is better hidden behind the
+                # backward even though that slows the backward's persistent kernels
+                overlap = "backward" if self.calibration_ms > 3.0 else "adam"
+        if overlap == "backward" and not staged_ok:
+            overlap = "none"
+        if overlap == "adam" and not sliced_ok:
+            overlap = "none"
+        self.overlap = overlap
         self._comm = None
         self._events = None
         self._sumsq = None
-        self._plan = plan_allreduce(model.gradient_stages(), allreduce_chunks) if self.overlap else None
+        self._plan = plan_allreduce(model.gradient_stages(), self.chunks) if overlap == "backward" else None
         dev = getattr(model, "device", torch.device("cpu"))
-        if self.world > 1 and self.overlap and dev.type == "cuda":
+        if self.world > 1 and overlap == "backward" and dev.type == "cuda":
             self._comm = torch.cuda.Stream(dev)
             wanted = {ev for _, _, ev in self._plan[:-1]}
             self._events = [torch.cuda.Event() if i in wanted else None
@@ -51,6 +78,29 @@ class SingleTaskTrainer:
             for e in self._events:
                 if e is not None:
                     e.record(torch.cuda.current_stream(dev))     # creates the cudaEvent_t the C ABI re-records
+
+    def _time_allreduce(self) -> float:
+        """Milliseconds of one all-reduce of the gradient bucket (max over ranks), after one warm-up call."""
+        g = self.model.flat_gradients
+        dist.all_reduce(g)
+        if g.device.type == "cuda":
+            torch.cuda.synchronize(g.device)
+        dist.barrier()
+        t0 = time.perf_counter()
+        dist.all_reduce(g)
+        if g.device.type == "cuda":
+            torch.cuda.synchronize(g.device)
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=g.device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        g.zero_()
+        return float(ms)
+
+    def even_slices(self):
+        """The bucket in `chunks` contiguous slices of equal size (16-byte aligned): the "adam" mode's transfer units."""
+        total = self.model.flat_gradients.numel()
+        step = -(-total // self.chunks)
+        step = (step + 7) // 8 * 8
+        return [(o, min(step, total - o)) for o in range(0, total, step)]
 
     def train_loop_begin(self):
         self.train_loss, self._steps = 0.0, 0
@@ -61,7 +111,7 @@ class SingleTaskTrainer:
         target = inputs.pop(self.label_key)                                     # :145
         clip = self.grad_clip_norm > 0
         reduce = self.world > 1 and self.allreduce
-        staged = reduce and self.overlap and not clip
+        staged = reduce and self.overlap == "backward" and not clip
         kw = {"stage_events": self._events} if staged and self._events else {}
         loss = self.model.forward_backward(inputs, target, loss_scale=1.0 / self.world, **kw)   # :151-158, 178
         grads = self.model.flat_gradients
@@ -80,9 +130,20 @@ class SingleTaskTrainer:
             else:
                 for off, cnt, _ in self._plan:
                     dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)
-        elif reduce:
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
-        self.optimizer.apply_gradients()
+            self.optimizer.apply_gradients()
+        elif reduce and self.overlap in ("adam", "backward") and hasattr(self.optimizer, "apply_range"):
+            # all slices go out back to back; the update of a slice follows its own transfer, not the whole bucket's
+            slices = self.even_slices()
+            works = [dist.all_reduce(grads[o:o + c], op=dist.ReduceOp.SUM, async_op=True) for o, c in slices]
+            self.optimizer.begin_step()
+            for (o, c), w in zip(slices, works):
+                w.wait()                                                        # stream-side wait for THIS slice only
+                self.optimizer.apply_range(o, c)
+            self.optimizer.end_step()
+        else:
+            if reduce:
+                dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+            self.optimizer.apply_gradients()
         self.model.global_step = self.optimizer.iterations
         return loss
 

@@ -230,3 +230,35 @@ def test_evaluator_writes_reference_layout(cuda, fact_lib, tmp_path):
     a = np.load(tmp_path / "gBR_sBM_c01_mBR0.npy")
     assert a.shape == (dims.motion_seq + 5, 225) and np.allclose(a[:dims.motion_seq], inp["motion_input"][0], atol=1e-6)
     assert (tmp_path / "gPO_sFM_c02_mPO1.npy").exists()
+
+
+def test_adam_in_slices_equals_adam_on_the_bucket(cuda, fact_lib):
+    """begin_step / apply_range over disjoint slices / end_step (what the data-parallel trainer does as all-reduce
+    slices land) is bit-identical to one apply_gradients over the bucket, including the bf16 operand copies."""
+    dims = oracle_dims(audio_dim=35, **SMALL)
+    inp = O.synthetic_inputs(dims, batch=2, seed=9, target_len=5)
+    tin = {k: torch.from_numpy(v).float() for k, v in inp.items()}
+    models, opts = [], []
+    for _ in range(2):
+        m = FACTModel(make_config(**SMALL), is_training=True, mode="bf16", seed=3)
+        models.append(m)
+        opts.append(Adam(m, learning_rate=3e-3))
+    for step in range(3):
+        for m in models:
+            m.forward_backward(tin, tin["target"])
+        assert torch.equal(models[0].flat_gradients, models[1].flat_gradients) or step > 0
+        models[1].flat_gradients.copy_(models[0].flat_gradients)       # identical inputs to both optimizers
+        opts[0].apply_gradients()
+        total = models[1].flat_parameters.numel()
+        cuts = [0, (total // 3) // 8 * 8, (2 * total // 3) // 8 * 8, total]
+        opts[1].begin_step()
+        for a, b in reversed(list(zip(cuts, cuts[1:]))):                # any order
+            opts[1].apply_range(a, b - a)
+        opts[1].end_step()
+        assert opts[0].iterations == opts[1].iterations == step + 1
+        assert torch.equal(models[0].flat_parameters, models[1].flat_parameters)
+        assert torch.equal(opts[0].m, opts[1].m) and torch.equal(opts[0].v, opts[1].v)
+        assert torch.equal(models[0].flat_bf16_parameters, models[1].flat_bf16_parameters)
+        models[1].flat_parameters.copy_(models[0].flat_parameters)
+    with pytest.raises(ValueError):
+        opts[1].apply_range(2, 8)

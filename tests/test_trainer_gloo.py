@@ -48,6 +48,26 @@ class _FakeOpt:
         return 1e-4
 
 
+class _SlicedOpt(_FakeOpt):
+    """Optimizer with the begin_step / apply_range / end_step protocol: records which slices were applied, in order,
+    and a copy of each slice AS IT WAS when its update ran (it must already hold the cross-replica sum)."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.ranges, self.seen_parts, self.ended = [], {}, 0
+
+    def begin_step(self):
+        self.iterations += 1
+
+    def apply_range(self, offset, count, grad_scale=1.0):
+        self.ranges.append((offset, count))
+        self.seen_parts[offset] = self.model.flat_gradients[offset:offset + count].clone()
+
+    def end_step(self):
+        self.ended += 1
+        self.seen = torch.cat([self.seen_parts[o] for o in sorted(self.seen_parts)])
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -62,6 +82,14 @@ def _worker(rank, world, port, q):
     o2 = _FakeOpt(m2)
     SingleTaskTrainer([], "target", m2, optimizer=o2).train_step({"motion_input": 0, "target": 1})
     ok = ok and torch.allclose(o2.seen, 1.5 * torch.arange(1.0, 9.0))
+    # "adam" mode: even slices, each updated right after its own all-reduce (async_op work.wait), covering the bucket
+    m6 = _FakeModel(rank)
+    o6 = _SlicedOpt(m6)
+    tr6 = SingleTaskTrainer([], "target", m6, optimizer=o6, overlap="adam", allreduce_chunks=3)
+    assert tr6.overlap == "adam"
+    tr6.train_step({"motion_input": 0, "target": 1})
+    ok = ok and o6.ended == 1 and sum(c for _, c in o6.ranges) == 8 and o6.ranges == sorted(o6.ranges)
+    ok = ok and torch.allclose(o6.seen, 1.5 * torch.arange(1.0, 9.0)) and m6.global_step == 1
     # clip BEFORE the sum (:180-183): each replica scales its own gradient to norm <= clip, then SUM
     m3 = _StagedModel(rank)
     o3 = _FakeOpt(m3)
