@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--train-batch", dest="train_batch", type=int, default=128,
                     help="clips per GPU of the training leg (BASELINE.json configs[2]/[3])")
     ap.add_argument("--no-train", action="store_true", help="skip the data-parallel training leg")
+    ap.add_argument("--dp-overlap", dest="dp_overlap", default="auto", choices=["auto", "fused", "adam", "backward", "none"],
+                    help="how the training leg hides its gradient all-reduce (mint_b200/trainer.py)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1->512 sweep leg (configs[4])")
     ap.add_argument("--sweep", default="1,2,4,8,16,32,64,128,256,512", help="clips per GPU of the sweep leg")
     ap.add_argument("--b1-frames", dest="b1_frames", type=int, default=1200,
@@ -367,13 +369,14 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
                       "global_batch": B * world, "products": "bf16 (fp32 accumulate, fp32 master weights / Adam state)",
                       "loss": "L2 motion loss on the first 20 frames", "optimizer": "Keras Adam",
                       "parallelism": f"dp{world}: one logical all-reduce of the flat fp32 gradient bucket per step, "
-                                     "issued as contiguous slices (allreduce_slices_mb) and hidden as allreduce_overlap "
-                                     "says: 'adam' = the Adam update of a slice runs while the next slice is on the "
-                                     "wire; 'backward' = slices follow the backward's stage events on a side stream"
+                                     "see allreduce_overlap: 'fused' = no all-reduce, ONE kernel sums the replicas' "
+                                     "gradients over NVLink peer memory, applies Adam to this rank's shard and stores "
+                                     "the new weights into every replica; 'adam' / 'backward' / 'none' = NCCL all-reduce "
+                                     "in slices hidden behind the optimizer pass / the backward / not at all"
                                      if world > 1 else "single GPU"}}
     with torch.cuda.stream(stream):
         batch_d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        dp = SingleTaskTrainer([], "target", model, optimizer=opt)
+        dp = SingleTaskTrainer([], "target", model, optimizer=opt, overlap=args.dp_overlap)
         local_only = SingleTaskTrainer([], "target", model, optimizer=opt, allreduce=False)
         losses = [dp.train_step(batch_d) for _ in range(Wm)]
         first_loss = float(losses[0])
@@ -447,8 +450,13 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
         "allreduce_ms": ar_ms, "exposed_allreduce_ms": exposed, "ms_per_step_without_allreduce": ms_local,
         "grad_bucket_mb": model.flat_gradients.numel() * 4 / 1e6,
         "allreduce_overlap": dp.overlap if world > 1 else None,
+        "allreduce_calibration_ms": dp.calibration_ms,
+        "fused_step": ({"kernel": "dp_adam_kernel (gradient sum + Adam + weight broadcast over peer memory)",
+                        "multicast": dp.arena.mc_ptr is not None, "arena_mb": dp.arena.nbytes / 1e6}
+                       if dp.arena is not None else {"unavailable": dp.fused_error}) if world > 1 else None,
         "allreduce_slices_mb": ([round(c * 4 / 1e6, 1) for _, c, _ in dp._plan] if dp._plan else
-                                [round(c * 4 / 1e6, 1) for _, c in dp.even_slices()]) if world > 1 else None,
+                                [round(c * 4 / 1e6, 1) for _, c in dp.even_slices()])
+        if world > 1 and dp.overlap != "fused" else None,
         "allreduce_busbw_gbs": (model.flat_gradients.numel() * 4 * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9
                                 if ar_ms else None),
         "gpu_topology": gpu_topology(world) if rank == 0 else None,

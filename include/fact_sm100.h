@@ -300,6 +300,22 @@ FACT_API int fact_cast_weight(const float* w_keras, void* out_bf16, int rows, in
 FACT_API int fact_adam_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1,
                             float beta2, float eps, long long step, float grad_scale, void* w_bf16, void* stream);
 
+/* Data-parallel optimizer step fused with its collective (single_task_trainer.py:186-187 + trainer.py:150): the
+ * cross-replica SUM of the gradients, the Keras Adam update and the re-mirroring of the variables in ONE kernel over
+ * NVLink peer memory.  Every replica keeps its flat gradient bucket, fp32 master weights and bf16 weight mirror inside
+ * one "arena" of symmetric memory (same layout on every rank); peer_base[p] is rank p's arena as mapped into this
+ * process (host array of `world` device pointers), grad_off / w_off / wb_off the byte offsets of the three arrays inside
+ * it.  mc_base: the NVSwitch multicast mapping of the arenas (multimem.ld_reduce / multimem.st: one load reduces over
+ * all replicas in the switch, one store reaches all of them), or NULL to loop over peer_base with P2P loads / stores.
+ * This rank updates elements [rank * per, (rank + 1) * per) of the n-element bucket, per = ceil(n / world) rounded up to
+ * a multiple of 8: it sums that shard of every replica's gradient, advances ITS shard of m / v (fp32 [n] arrays local
+ * to this rank: optimizer state is sharded, the other shards are never touched) and stores the new weights -- fp32 and
+ * bf16 -- into every replica.  The caller must put a cross-replica barrier before the call (all gradients final) and
+ * after it (all stores landed); world <= 16.  Same arithmetic as fact_adam_step. */
+FACT_API int fact_dp_adam_step(void* const* peer_base, void* mc_base, long long grad_off, long long w_off,
+                               long long wb_off, float* m, float* v, long long n, int rank, int world, float lr,
+                               float beta1, float beta2, float eps, long long step, float grad_scale, void* stream);
+
 /* *out = sum g^2 (for clip_by_global_norm, single_task_trainer.py:180-183). */
 FACT_API int fact_sum_squares(const float* g, long long n, float* out, void* stream);
 

@@ -651,6 +651,77 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
   }
 }
 
+// ---- data-parallel optimizer step fused with its collective, over NVLink peer memory --------------------------------
+// What the reference does in three framework steps -- cross-replica SUM of the gradients (MirroredStrategy inside
+// apply_gradients, single_task_trainer.py:186-187), Keras Adam (trainer.py:150), variables mirrored on every replica --
+// is ONE kernel here.  Every rank owns a 1/world shard of the flat bucket and, for the elements of its shard:
+//   reduce     g = sum over replicas of their local gradient       (P2P loads from every peer's bucket, or ONE
+//                                                                    multimem.ld_reduce through the NVSwitch multicast)
+//   update     m, v, w  (the Adam moments of a shard live only on its owner: optimizer state is sharded)
+//   broadcast  w (fp32 master) and bf16(w) (the operand mirror) stored into EVERY replica's buffers
+//                                                                   (P2P stores, or ONE multimem.st each)
+// so a gradient element crosses the fabric once and the new weight once; there is no separate all-reduce, no second
+// pass over the bucket, and replicas stay bit-identical because all of them receive the same stored values.
+// The host brackets the launch with two device-side barriers over the symmetric memory (all gradients final before,
+// all stores landed after).
+constexpr int DP_MAX_WORLD = 16;
+struct DpPeers {
+  char* base[DP_MAX_WORLD];  // arena of rank p as mapped into THIS process
+};
+
+__device__ __forceinline__ float4 ld_f4(const char* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <bool MC>
+__global__ void __launch_bounds__(256) dp_adam_kernel(DpPeers peers, char* mc_base, long long grad_off, long long w_off,
+                                                      long long wb_off, float* __restrict__ m, float* __restrict__ v,
+                                                      long long lo, long long hi, int rank, int world, float lr_t,
+                                                      float b1, float b2, float eps, float grad_scale) {
+  // elements [lo, hi) of the bucket, four per thread (lo and hi are multiples of 4)
+  for (long long i = lo + 4 * (blockIdx.x * 256ll + threadIdx.x); i < hi; i += 4 * 256ll * gridDim.x) {
+    float4 g;
+    if (MC) {
+      const char* a = mc_base + grad_off + 4 * i;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+                   : "l"(a)
+                   : "memory");
+    } else {
+      g = ld_f4(peers.base[0] + grad_off + 4 * i);
+      for (int p = 1; p < world; ++p) {  // fixed order: every run sums the replicas the same way
+        const float4 t = ld_f4(peers.base[p] + grad_off + 4 * i);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    const float4 w0 = ld_f4(peers.base[rank] + w_off + 4 * i);
+    float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+    float gg[4] = {g.x * grad_scale, g.y * grad_scale, g.z * grad_scale, g.w * grad_scale};
+    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, wa[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ma[e] = b1 * ma[e] + (1.f - b1) * gg[e];
+      va[e] = b2 * va[e] + (1.f - b2) * gg[e] * gg[e];
+      wa[e] = wa[e] - lr_t * ma[e] / (sqrtf(va[e]) + eps);
+    }
+    *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
+    const uint32_t h0 = cvt_bf16x2(wa[0], wa[1]), h1 = cvt_bf16x2(wa[2], wa[3]);
+    if (MC) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_base + w_off + 4 * i),
+                   "f"(wa[0]), "f"(wa[1]), "f"(wa[2]), "f"(wa[3])
+                   : "memory");
+      asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc_base + wb_off + 2 * i),
+                   "f"(__uint_as_float(h0)), "f"(__uint_as_float(h1))
+                   : "memory");
+    } else {
+      for (int p = 0; p < world; ++p) {
+        *reinterpret_cast<float4*>(peers.base[p] + w_off + 4 * i) = make_float4(wa[0], wa[1], wa[2], wa[3]);
+        *reinterpret_cast<uint2*>(peers.base[p] + wb_off + 2 * i) = make_uint2(h0, h1);
+      }
+    }
+  }
+  __threadfence_system();
+}
+
 // sum of squares (global-norm clipping, single_task_trainer.py:180-183)
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   float s = 0.f;
@@ -967,6 +1038,42 @@ extern "C" int fact_adam_step(float* w, const float* g, float* m, float* v, long
   adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale,
                                                    static_cast<bf16*>(w_bf16));
   FACT_LAUNCH_CHECK("adam_kernel");
+  return FACT_OK;
+}
+
+extern "C" int fact_dp_adam_step(void* const* peer_base, void* mc_base, long long grad_off, long long w_off,
+                                 long long wb_off, float* m, float* v, long long n, int rank, int world, float lr,
+                                 float beta1, float beta2, float eps, long long step, float grad_scale, void* stream) {
+  FACT_REQUIRE(peer_base && m && v && n > 0 && step >= 1, FACT_ERR_BAD_SHAPE, "fact_dp_adam_step: bad arguments");
+  FACT_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, FACT_ERR_BAD_SHAPE,
+               "fact_dp_adam_step: rank %d of %d (at most %d replicas)", rank, world, DP_MAX_WORLD);
+  FACT_REQUIRE(grad_off % 16 == 0 && w_off % 16 == 0 && wb_off % 16 == 0 && n % 4 == 0, FACT_ERR_BAD_ALIGN,
+               "fact_dp_adam_step: offsets must be 16-byte aligned and n a multiple of 4");
+  DpPeers peers{};
+  for (int p = 0; p < world; ++p) {
+    FACT_REQUIRE(peer_base[p] != nullptr && (reinterpret_cast<uintptr_t>(peer_base[p]) & 15) == 0, FACT_ERR_BAD_ALIGN,
+                 "fact_dp_adam_step: arena of rank %d is null or misaligned", p);
+    peers.base[p] = static_cast<char*>(peer_base[p]);
+  }
+  // shard r = elements [r * per, min(n, (r + 1) * per)), per a multiple of 8 (16-byte bf16 stores)
+  long long per = (n + world - 1) / world;
+  per = (per + 7) / 8 * 8;
+  const long long lo = per * rank < n ? per * rank : n, hi = lo + per < n ? lo + per : n;
+  if (hi <= lo) return FACT_OK;
+  const double t = static_cast<double>(step);
+  const float lr_t = static_cast<float>(lr * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
+                                        (1.0 - pow(static_cast<double>(beta1), t)));
+  const long long threads = (hi - lo) / 4;
+  long long blocks = (threads + 255) / 256;
+  const int grid = static_cast<int>(blocks > 4096 ? 4096 : blocks);
+  if (mc_base)
+    dp_adam_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(peers, static_cast<char*>(mc_base), grad_off, w_off, wb_off,
+                                                              m, v, lo, hi, rank, world, lr_t, beta1, beta2, eps,
+                                                              grad_scale);
+  else
+    dp_adam_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(peers, nullptr, grad_off, w_off, wb_off, m, v, lo, hi, rank,
+                                                               world, lr_t, beta1, beta2, eps, grad_scale);
+  FACT_LAUNCH_CHECK("dp_adam_kernel");
   return FACT_OK;
 }
 

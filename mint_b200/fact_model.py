@@ -345,6 +345,30 @@ class FACTModel:
         self.repack()
         self._build_grad_tables()
 
+    def adopt_symmetric(self, arena) -> None:
+        """Move the flat parameter bucket, the gradient bucket and the bf16 mirror into `arena`
+        (mint_b200.parallel.SymmetricArena) so that peers can read / write them over NVLink; the named variables,
+        gradients and operand copies become views of the arena.  Values are preserved."""
+        self._ensure_training_state()
+        n = self._flat.numel()
+        if arena.numel != n:
+            raise ValueError("arena size does not match the parameter bucket")
+        arena.w.copy_(self._flat)
+        arena.grad.copy_(self._grad_flat)
+        arena.wb.copy_(self._kl_flat)
+        self._flat, self._grad_flat, self._kl_flat = arena.w, arena.grad, arena.wb
+        self._kl_end = self._kl_flat.data_ptr() + 2 * n
+        for name, p in list(self._params.items()):
+            o, cnt = self._offsets[name]
+            shp = tuple(p.shape)
+            self._params[name] = self._flat[o:o + cnt].view(shp)
+            self._grads[name] = self._grad_flat[o:o + cnt].view(shp)
+            if name in self._keras_bf16 and name != "cross_modal_layer/output/kernel":
+                self._keras_bf16[name] = self._kl_flat[o:o + cnt].view(shp)
+        self._arena = arena               # keeps the symmetric allocation alive as long as the model
+        self.repack()
+        self._build_grad_tables()
+
     def _build_grad_tables(self) -> None:
         G, d = self._grads, self.dims
 

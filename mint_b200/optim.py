@@ -102,8 +102,37 @@ class Adam:
     def end_step(self) -> None:
         self.model.repack(bf16_copy_done=self.model.flat_bf16_parameters is not None)
 
+    def dp_fused_step(self, arena, grad_scale: float = 1.0) -> None:
+        """Cross-replica gradient sum + Adam + weight broadcast in ONE kernel over peer memory (fact_dp_adam_step).
+        The caller brackets it with arena.barrier() and calls end_step() afterwards.  From the first call on this
+        rank's m / v are meaningful only inside arena.shard() (sharded optimizer state; state_dict() reassembles)."""
+        import ctypes as C
+        self.begin_step()
+        self._sharded = arena
+        with torch.cuda.device(self.model.device):
+            st = torch.cuda.current_stream(self.model.device).cuda_stream
+            lib.check(self._lib.fact_dp_adam_step(
+                arena.peer_ptrs, arena.mc_ptr, arena.grad_off, arena.w_off, arena.wb_off, self.m.data_ptr(),
+                self.v.data_ptr(), arena.numel, arena.rank, arena.world, self._lr, self.beta_1, self.beta_2,
+                self.epsilon, self.iterations, float(grad_scale), st), "fact_dp_adam_step")
+
+    def _mask_to_shard(self, t: torch.Tensor) -> torch.Tensor:
+        lo, cnt = self._sharded.shard()
+        out = torch.zeros_like(t)
+        out[lo:lo + cnt] = t[lo:lo + cnt]
+        return out
+
     def state_dict(self):
-        return {"iterations": self.iterations, "m": self.m, "v": self.v}
+        """COLLECTIVE when the state is sharded (after dp_fused_step): every rank calls it, every rank gets the full
+        moments (each shard comes from its owner: a SUM all-reduce of the masked arrays)."""
+        arena = getattr(self, "_sharded", None)
+        if arena is None:
+            return {"iterations": self.iterations, "m": self.m, "v": self.v}
+        import torch.distributed as dist
+        m, v = self._mask_to_shard(self.m), self._mask_to_shard(self.v)
+        dist.all_reduce(m)
+        dist.all_reduce(v)
+        return {"iterations": self.iterations, "m": m, "v": v}
 
     def load_state_dict(self, sd):
         self.iterations = int(sd["iterations"])

@@ -4,8 +4,17 @@ Same step semantics: pop the label, forward, `loss / num_replicas`, gradients, o
 clip_by_global_norm BEFORE the cross-replica sum (single_task_trainer.py:180-183), one SUM all-reduce of all gradients
 (what MirroredStrategy does inside apply_gradients, :186-187), Adam.  One process per GPU.
 
-The cross-replica sum is ONE logical all-reduce of the model's flat gradient bucket, issued as a few contiguous slices.
-Two ways to hide it, chosen by `overlap` ("auto" times one all-reduce of the bucket at construction):
+How the cross-replica sum happens is chosen by `overlap`:
+
+  "fused"     (default wherever torch symmetric memory can map the replicas' buffers into each other: NVLink /
+              NVSwitch boxes).  No all-reduce at all: the gradient sum, the Adam update and the mirroring of the new
+              weights are ONE hand-written kernel over peer memory (fact_dp_adam_step: each rank reduces and updates a
+              1/world shard -- one multimem.ld_reduce through the NVSwitch multicast per 16 bytes, or P2P loads -- and
+              stores the new fp32 / bf16 weights into every replica), bracketed by two device-side barriers.  The
+              optimizer moments are sharded (each rank keeps its shard only; Adam.state_dict() reassembles them).
+
+Otherwise the sum is ONE logical NCCL all-reduce of the model's flat gradient bucket, issued as a few contiguous slices,
+hidden in one of two ways ("auto" times one all-reduce of the bucket at construction):
 
   "adam"      (fast links: NVLink / NVSwitch, the all-reduce is about as long as the optimizer pass).  All slices are
               issued right after the backward; the Adam update of slice i runs as soon as slice i has landed, while
@@ -48,11 +57,19 @@ class SingleTaskTrainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.allreduce = allreduce
         self.chunks = max(1, int(allreduce_chunks))
-        if overlap not in ("auto", "adam", "backward", "none"):
-            raise ValueError("overlap must be auto, adam, backward or none")
+        if overlap not in ("auto", "fused", "adam", "backward", "none"):
+            raise ValueError("overlap must be auto, fused, adam, backward or none")
         staged_ok = hasattr(model, "gradient_stages")
         sliced_ok = hasattr(optimizer, "apply_range")
         self.calibration_ms = None
+        self.arena, self.fused_error = None, None
+        if overlap in ("auto", "fused") and self.world > 1 and allreduce and hasattr(model, "adopt_symmetric") \
+                and hasattr(optimizer, "dp_fused_step"):
+            self.arena, self.fused_error = _make_arena(model)
+            if self.arena is not None:
+                overlap = "fused"
+        if overlap == "fused" and self.arena is None:
+            overlap = "auto"                                   # symmetric memory unavailable: NCCL paths below
         if overlap == "auto":
             overlap = "adam" if sliced_ok else ("backward" if staged_ok else "none")
             if self.world > 1 and allreduce and staged_ok and sliced_ok:
@@ -117,7 +134,12 @@ class SingleTaskTrainer:
         grads = self.model.flat_gradients
         if clip:                                                                # :180-183, per replica, before the sum
             clip_by_global_norm_(self.model, self.grad_clip_norm, self)
-        if staged:                                                              # :186-187 (cross-replica SUM)
+        if reduce and self.overlap == "fused":                                  # :186-187 + Adam + re-mirroring, fused
+            self.arena.barrier()                    # every replica's gradients are final
+            self.optimizer.dp_fused_step(self.arena)
+            self.arena.barrier()                    # every replica's stores into my weights have landed
+            self.optimizer.end_step()
+        elif staged:                                                            # :186-187 (cross-replica SUM)
             if self._comm is not None:
                 cur = torch.cuda.current_stream(grads.device)
                 with torch.cuda.stream(self._comm):
@@ -173,6 +195,23 @@ class SingleTaskTrainer:
         dt = time.perf_counter() - self._t0
         return {"training_loss": mean, "task_loss": mean, "regularization_loss": 0.0,
                 "learning_rate": self.optimizer.current_lr(), "steps_per_second": n / dt if dt > 0 else float("nan")}
+
+
+def _make_arena(model):
+    """(arena, None) with the model's buckets moved into symmetric memory on EVERY rank, or (None, reason)."""
+    from .parallel import SymmetricArena
+    arena, err = None, None
+    try:
+        arena = SymmetricArena(model.flat_parameters.numel(), model.device)
+    except Exception as exc:                                   # no symmetric memory on this box / build: NCCL instead
+        err = repr(exc)[:300]
+    ok = torch.tensor([0 if arena is None else 1], dtype=torch.int32, device=model.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)                  # all or nobody
+    if int(ok) == 0:
+        return None, err or "symmetric memory unavailable on another rank"
+    model.adopt_symmetric(arena)
+    arena.barrier()
+    return arena, None
 
 
 def plan_allreduce(stages, chunks: int):

@@ -100,11 +100,13 @@ def main():
         while opt.iterations < args.steps:
             n = min(args.steps_per_loop, args.steps - opt.iterations)
             logs = trainer.train(n)
+            saving = opt.iterations % args.checkpoint_interval == 0 or opt.iterations == args.steps
+            opt_state = opt.state_dict() if saving else None      # collective when the moments are sharded ("fused")
             if rank == 0:
                 print(json.dumps({"step": opt.iterations, **logs}), flush=True)
-                if opt.iterations % args.checkpoint_interval == 0 or opt.iterations == args.steps:
+                if saving:
                     path = os.path.join(args.model_dir, "ckpt-%09d.pt" % opt.iterations)
-                    torch.save({"flat_parameters": model.flat_parameters, "optimizer": opt.state_dict(),
+                    torch.save({"flat_parameters": model.flat_parameters, "optimizer": opt_state,
                                 "names": model.variable_names()}, path)
                     if args.export_tf_checkpoint:
                         from mint_b200 import tf_checkpoint
