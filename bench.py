@@ -401,12 +401,30 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
         ms, t0, t1, last = timed(lambda: dp.train_step(batch_d), K)
         launches = L.load().fact_launch_count() - launches0
         clocks = sampler.stop(t0, t1) if rank == 0 else None
-        ar_ms = exposed = ms_local = None
+        ar_ms = exposed = ms_local = ms_sync = None
+        modes = None
         if world > 1:
+            # Decomposition, all in this process on the same clocks: free-running replicas (no cross-replica op),
+            # replicas that only MEET once per step (4-byte all-reduce: pure synchronisation skew -- power-capped GPUs
+            # do not run at one clock), and every way of moving the gradients this box supports.
+            synced = SingleTaskTrainer([], "target", model, optimizer=opt, allreduce=False, sync_only=True)
             ms_local, _, _, _ = timed(lambda: local_only.train_step(batch_d), K)
-            ms2, _, _, _ = timed(lambda: dp.train_step(batch_d), K)     # again, so both sides see the same clocks
-            ms_dp = min(ms, ms2)
-            exposed = ms_dp - ms_local
+            # clocks drift while the GPU warms up under its power cap, so every mode is bracketed by two runs of the
+            # meet-only step and compared with their mean
+            modes = {}
+            sync_runs = [timed(lambda: synced.train_step(batch_d), K)[0]]
+            for mode in (["fused"] if dp.arena is not None else []) + ["none", "adam", "backward"]:
+                tr = dp if mode == dp.overlap else SingleTaskTrainer([], "target", model, optimizer=opt, overlap=mode,
+                                                                      arena=dp.arena if mode == "fused" else None)
+                for _ in range(2):
+                    tr.train_step(batch_d)
+                m_ms, _, _, _ = timed(lambda: tr.train_step(batch_d), K)
+                sync_runs.append(timed(lambda: synced.train_step(batch_d), K)[0])
+                ref = 0.5 * (sync_runs[-2] + sync_runs[-1])
+                modes[mode] = {"ms_per_step": m_ms, "meet_only_ms_per_step": ref, "exposed_ms": m_ms - ref}
+            ms_sync = sum(sync_runs) / len(sync_runs)
+            ms = modes[dp.overlap]["ms_per_step"]
+            exposed = modes[dp.overlap]["exposed_ms"]
             grads = model.flat_gradients
 
             def ar():
@@ -447,7 +465,14 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
         "ms_per_step": ms, "samples_per_s": world * B * 1e3 / ms, "steps": K, "warmup": Wm,
         "algorithmic_tflops_per_gpu": TRAIN_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12,
         "frac_of_sustained_tensor_peak": TRAIN_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
-        "allreduce_ms": ar_ms, "exposed_allreduce_ms": exposed, "ms_per_step_without_allreduce": ms_local,
+        "allreduce_ms": ar_ms, "exposed_allreduce_ms": exposed, "ms_per_step_without_allreduce": ms_sync,
+        "ms_per_step_free_running": ms_local,
+        "sync_skew_ms": (ms_sync - ms_local) if ms_sync is not None else None,
+        "modes": modes,
+        "exposed_note": ("exposed_allreduce_ms = data-parallel step - step in which the replicas only meet (4-byte "
+                         "all-reduce); sync_skew_ms = that step - free-running replicas (max over ranks of the mean): "
+                         "the price of lock step under per-GPU power caps, paid by any synchronous scheme") if world > 1
+        else None,
         "grad_bucket_mb": model.flat_gradients.numel() * 4 / 1e6,
         "allreduce_overlap": dp.overlap if world > 1 else None,
         "allreduce_calibration_ms": dp.calibration_ms,

@@ -41,10 +41,13 @@ import torch.distributed as dist
 class SingleTaskTrainer:
     def __init__(self, train_dataset, label_key, model, loss_fn=None, optimizer=None, metrics=None,
                  trainer_options=None, summary_fn=None, grad_clip_norm: float = 0.0, overlap: str = "auto",
-                 allreduce: bool = True, allreduce_chunks: int = 8):
+                 allreduce: bool = True, allreduce_chunks: int = 4, sync_only: bool = False, arena=None):
         """train_dataset: iterable of dict batches (torch / numpy); label_key: 'target' (trainer.py:157).
         overlap: "auto" | "adam" | "backward" | "none" (see the module docstring).
-        allreduce=False skips the cross-replica sum (bench.py uses it to measure how much of it is exposed)."""
+        allreduce=False skips the cross-replica sum; sync_only=True then still makes the replicas meet once per step
+        (a 4-byte all-reduce): bench.py subtracts that step from the data-parallel one, so what is left is the cost of
+        moving the gradients, not the skew of replicas whose clocks differ under their power caps.
+        arena: a SymmetricArena the model already lives in (another trainer of the same model made it)."""
         self.train_dataset = train_dataset
         self.label_key = label_key
         self.model = model
@@ -62,10 +65,13 @@ class SingleTaskTrainer:
         staged_ok = hasattr(model, "gradient_stages")
         sliced_ok = hasattr(optimizer, "apply_range")
         self.calibration_ms = None
-        self.arena, self.fused_error = None, None
+        self.sync_only = bool(sync_only) and not allreduce
+        self._sync_word = None
+        self.arena, self.fused_error = arena, None
         if overlap in ("auto", "fused") and self.world > 1 and allreduce and hasattr(model, "adopt_symmetric") \
                 and hasattr(optimizer, "dp_fused_step"):
-            self.arena, self.fused_error = _make_arena(model)
+            if self.arena is None:
+                self.arena, self.fused_error = _make_arena(model)
             if self.arena is not None:
                 overlap = "fused"
         if overlap == "fused" and self.arena is None:
@@ -165,6 +171,10 @@ class SingleTaskTrainer:
         else:
             if reduce:
                 dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+            elif self.sync_only and self.world > 1:
+                if self._sync_word is None:
+                    self._sync_word = torch.zeros(1, dtype=torch.float32, device=grads.device)
+                dist.all_reduce(self._sync_word)                               # replicas meet, nothing moves
             self.optimizer.apply_gradients()
         self.model.global_step = self.optimizer.iterations
         return loss
