@@ -283,6 +283,14 @@ def kernel_rooflines(model, batch, mode, peaks, stream):
              ("gemm_out", gemm(a_d, w["o"], M, d, d, e_o), 2.0 * M * d * d),
              ("gemm_ff1", gemm(a_d, w["ff1"], M, ff, d, e_ff1), 2.0 * M * ff * d),
              ("gemm_ff2", gemm(a_ff, w["ff2"], M, d, ff, e_ff2), 2.0 * M * d * ff)]
+    # the residual GEMMs as the model calls them: LayerNorm of the finished rows inside the launch (LayerNorm warps)
+    gam, bet = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    ln_sync = torch.zeros(M // 32 + 2, dtype=torch.int32, device=dev)
+    e_o_ln = L.GemmEpilogue(kind=L.EPI_BIAS_RESID_F32, out_f32=x.data_ptr(), ldo=d, bias=bias_d.data_ptr(),
+                            resid=x.data_ptr(), ldr=d, ln_gamma=gam.data_ptr(), ln_beta=bet.data_ptr(),
+                            ln_hi=out_d[0].data_ptr(), ln_lo=lo(out_d), ln_sync=ln_sync.data_ptr())
+    specs += [("gemm_out_ln", gemm(a_d, w["o"], M, d, d, e_o_ln), 2.0 * M * d * d),
+              ("gemm_ff2_ln", gemm(a_ff, w["ff2"], M, d, ff, e_o_ln), 2.0 * M * d * ff)]
     mult = 3.0 if precise else 1.0
     for name, fn, flops in specs:
         t = time_kernel(fn, stream)
@@ -301,7 +309,9 @@ def kernel_rooflines(model, batch, mode, peaks, stream):
     t = time_kernel(ln, stream)
     res["layernorm_split"] = {"s": t, "gbs": (M * d * 4.0 + M * d * s_el) / t / 1e9}
     # fused attention block as the metric defines it: x in + y out + weights, nothing else
-    t_blk = res["layernorm_split"]["s"] + res["gemm_qkv"]["s"] + res["sdpa"]["s"] + res["gemm_out"]["s"]
+    # LN + QKV + core + out-proj; the LayerNorm rides inside a residual GEMM launch when that is the faster pairing
+    t_out_ln = min(res["gemm_out_ln"]["s"], res["layernorm_split"]["s"] + res["gemm_out"]["s"])
+    t_blk = res["gemm_qkv"]["s"] + res["sdpa"]["s"] + t_out_ln
     blk_bytes = 1600.0 * batch * n_seq * 4 + 2562400.0 * s_el
     blk_flops = mult * (2.0 * M * 3 * d * d + 2.0 * M * d * d + 3200.0 * n_seq * n_seq * batch)
     blk_bytes_s2 = 1600.0 * batch * n_seq * 2 + 2562400.0 * 2
@@ -577,6 +587,9 @@ def run_ours(args):
             kr = kernel_rooflines(model, args.batch, args.mode, peaks, stream)
         for k, v in kr.items():
             print(k, {kk: round(vv, 6) for kk, vv in v.items()})
+        with torch.cuda.stream(stream):
+            t_w, fl = time_wgrad(model, args.batch, stream)
+        print("wgrad_ff", {"s": round(t_w, 6), "tflops": round(fl / t_w / 1e12, 1)})
         return
 
     def barrier():
@@ -697,7 +710,7 @@ def run_ours(args):
                          "algorithmic = 2*M*N*K of the fp32-grade product") if args.mode == "precise" else "bf16",
             }
             extras["attn_roofline"] = {
-                "bound": "hbm", "kernel": "attention block = ln_split_kernel, gemm_tc_kernel (QKV), sdpa_tc_kernel, gemm_tc_kernel (out-proj)",
+                "bound": "hbm", "kernel": "attention block = gemm_tc2_kernel (QKV), sdpa_tc_kernel, gemm_tc2_kernel (out-proj + bias + residual, LayerNorm of the finished rows by the kernel's own LayerNorm warps)",
                 "achieved": kr["attn_block"]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": kr["attn_block"]["frac_hbm"],
                 "sdpa_core_gbs": kr["sdpa"]["gbs"], "sdpa_core_frac": kr["sdpa"]["gbs"] / peaks["hbm_gbs"],

@@ -40,7 +40,7 @@ extern "C" {
 #define FACT_MODE_BF16 1
 #define FACT_MODE_FP32_SIMT 2
 
-#define FACT_ABI_VERSION 3
+#define FACT_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define FACT_API __attribute__((visibility("default")))
@@ -187,6 +187,12 @@ typedef struct fact_gemm_epilogue {
   const float* ln_beta;
   void* ln_hi;
   void* ln_lo;
+  /* optional with ln_hi: (m + 31) / 32 ints, zero before the first call and left zero by every call.  With it, large
+   * problems (CTA-pair path, n a multiple of 160) normalise their rows INSIDE the GEMM launch: dedicated warps wait
+   * until all column tiles of a 32-row group have landed (arrival counters in ln_sync) and write the bf16 hi / lo
+   * rows while the tensor pipe works on the next tiles -- no LayerNorm launch, no second HBM read of the residual
+   * stream.  Calls that share an ln_sync array must be ordered on one stream.  NULL = LayerNorm as its own launch. */
+  int* ln_sync;
 } fact_gemm_epilogue;
 
 /* C[m,n] = A[m,k] . W[n,k]^T on the tcgen05 tensor path (TMA-staged, TMEM accumulators).

@@ -35,59 +35,10 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
   pdl_trigger();
   pdl_wait();
   if (row >= rows) return;
-  const int nv = d >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
   float4 v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = lane + i * 32;
-    v[i] = idx < nv ? __ldg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float mean = 0.f, rstd = 1.f;
-  if (NORM) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    mean = s / static_cast<float>(d);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (lane + i * 32 < nv) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-        q += (a * a + b * b) + (c * c + e * e);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    rstd = rsqrtf(q / static_cast<float>(d) + 1e-5f);
-  }
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-  uint2* hr = reinterpret_cast<uint2*>(hi + static_cast<size_t>(row) * d);
-  uint2* lr = lo ? reinterpret_cast<uint2*>(lo + static_cast<size_t>(row) * d) : nullptr;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      float4 y = v[i];
-      if (NORM) {
-        const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
-        y.x = (y.x - mean) * rstd * gg.x + bb.x;
-        y.y = (y.y - mean) * rstd * gg.y + bb.y;
-        y.z = (y.z - mean) * rstd * gg.z + bb.z;
-        y.w = (y.w - mean) * rstd * gg.w + bb.w;
-      }
-      bf16 h0, h1, h2, h3, l0, l1, l2, l3;
-      split_bf16(y.x, h0, l0);
-      split_bf16(y.y, h1, l1);
-      split_bf16(y.z, h2, l2);
-      split_bf16(y.w, h3, l3);
-      hr[idx] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-      if (lr) lr[idx] = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-    }
-  }
+  ln_row_load<false>(x + static_cast<size_t>(row) * d, d >> 2, lane, v);
+  ln_row_finish<NORM>(v, gamma, beta, hi + static_cast<size_t>(row) * d, lo ? lo + static_cast<size_t>(row) * d : nullptr,
+                      d, lane);
 }
 
 // ------------------------------------------------------------------------------------------- weight packing

@@ -34,6 +34,10 @@ struct Workspace {
   bf16 *a_ln_hi, *a_ln_lo, *a_ao_hi, *a_ao_lo, *a_qkv_hi, *a_qkv_lo, *a_h_hi, *a_h_lo;
   float* a_splitk;
   size_t a_splitk_bytes;
+  // arrival counters of the GEMMs that normalise their own output rows (fact_gemm_epilogue.ln_sync): one int per 32
+  // rows, zeroed at the start of every API call, left zero by every GEMM; the concurrent audio encoder has its own
+  int *ln_sync, *a_ln_sync;
+  size_t ln_sync_bytes, a_ln_sync_bytes;
   // tensor-core embedding (batch * seq >= kEmbedTcMinRows): split inputs and packed LinearEmbedding kernels
   bf16 *em_x_hi, *em_x_lo, *ea_x_hi, *ea_x_lo;   // [tokens, kp]
   bf16 *em_w_hi, *em_w_lo, *ea_w_hi, *ea_w_lo;   // [d, kp]
@@ -73,6 +77,8 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
   // up to 16 slabs of the widest small-M GEMM output (GEMMs with m <= 1024: batch-1/2 decode, the row-0 AR tail)
   w.splitk_bytes = 16 * (tc < 1024 ? tc : 1024) * (3 * d > ff ? 3 * d : ff) * 4;
   w.splitk = reinterpret_cast<float*>(take(w.splitk_bytes));
+  w.ln_sync_bytes = ((tc + 31) / 32 + 1) * sizeof(int);
+  w.ln_sync = reinterpret_cast<int*>(take(w.ln_sync_bytes));
   if (ta <= kDualStreamMaxTokens) {
     w.a_ln_hi = reinterpret_cast<bf16*>(take(ta * d * 2));
     w.a_ln_lo = lo ? reinterpret_cast<bf16*>(take(ta * d * 2)) : nullptr;
@@ -84,6 +90,8 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
     w.a_h_lo = lo ? reinterpret_cast<bf16*>(take(ta * ff * 2)) : nullptr;
     w.a_splitk_bytes = 16 * (ta < 1024 ? ta : 1024) * (3 * d > ff ? 3 * d : ff) * 4;
     w.a_splitk = reinterpret_cast<float*>(take(w.a_splitk_bytes));
+    w.a_ln_sync_bytes = ((ta + 31) / 32 + 1) * sizeof(int);
+    w.a_ln_sync = reinterpret_cast<int*>(take(w.a_ln_sync_bytes));
   }
   if (mode != FACT_MODE_FP32_SIMT && tm >= kEmbedTcMinRows) {
     w.em_kp = (dm->motion_dim + 7) / 8 * 8;
@@ -99,6 +107,13 @@ static size_t carve(const fact_dims* dm, int batch, int mode, void* base, Worksp
   }
   if (ws) *ws = w;
   return off;
+}
+
+// once per API call, outside any captured frame
+static int zero_ln_sync(const Workspace& ws, cudaStream_t st) {
+  FACT_CUDA_CHECK(cudaMemsetAsync(ws.ln_sync, 0, ws.ln_sync_bytes, st));
+  if (ws.a_ln_sync) FACT_CUDA_CHECK(cudaMemsetAsync(ws.a_ln_sync, 0, ws.a_ln_sync_bytes, st));
+  return FACT_OK;
 }
 
 static int check_dims(const fact_dims* dm) {
@@ -170,6 +185,7 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
     e.ln_beta = L.ln2_beta;
     e.ln_hi = ws.ln_hi;
     e.ln_lo = lo ? ws.ln_lo : nullptr;
+    e.ln_sync = ws.ln_sync;
   }
   if ((rc = dense(mode, ws.ao_hi, ws.ao_lo, d, L.wo_hi, L.wo_lo, L.wo_f32, M, d, d, &e, st, &ws))) return rc;
   if (!ride &&
@@ -198,6 +214,7 @@ static int run_layer(const fact_dims* dm, const fact_layer_weights& L, float* x,
     e.ln_beta = next->ln1_beta;
     e.ln_hi = ws.ln_hi;
     e.ln_lo = lo ? ws.ln_lo : nullptr;
+    e.ln_sync = ws.ln_sync;
   }
   return dense(mode, ws.h_hi, ws.h_lo, ff, L.w2_hi, L.w2_lo, L.w2_f32, M, d, ff, &e, st, &ws);
 }
@@ -346,6 +363,7 @@ static int run_trunk(const fact_dims* dm, const fact_weights* w, const float* mo
     wa.ln_hi = ws.a_ln_hi; wa.ln_lo = ws.a_ln_lo; wa.ao_hi = ws.a_ao_hi; wa.ao_lo = ws.a_ao_lo;
     wa.qkv_hi = ws.a_qkv_hi; wa.qkv_lo = ws.a_qkv_lo; wa.h_hi = ws.a_h_hi; wa.h_lo = ws.a_h_lo;
     wa.splitk = ws.a_splitk; wa.splitk_bytes = ws.a_splitk_bytes;
+    wa.ln_sync = ws.a_ln_sync;
     FACT_CUDA_CHECK(cudaEventRecord(ev_fork, st));
     FACT_CUDA_CHECK(cudaStreamWaitEvent(sa, ev_fork, 0));
     if ((rc = embed(audio, audio_bs, step_ptr, w->audio_embed_w, w->audio_embed_b, w->audio_pos, ws.xa, batch,
@@ -391,7 +409,8 @@ static int check_weights(const fact_dims* dm, const fact_weights* w) {
 // ---- graph cache for the AR loop
 int g_ar_prune = 1;  // fact_set_flag("ar_prune", 0): run the full last layer (A-B check of the row-0 pruning)
 int g_ar_fused = 1;  // reserved for the fused small-batch decode path (fact_set_flag("ar_fused", 0) disables it)
-extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn, g_gemm_finish_ln;
+extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn, g_gemm_finish_ln, g_sdpa_wide,
+    g_gemm_fuse_ln;
 
 // One captured frame is valid for exactly the pointers and sizes it was captured with, so the key is EVERYTHING the
 // capture bakes in: the whole weight table (every pointer of every layer), the dims, every developer flag, the call's
@@ -457,6 +476,7 @@ extern "C" int fact_forward(const fact_dims* dims, const fact_weights* w, const 
   const long long mbs = static_cast<long long>(dims->motion_seq) * dims->motion_dim;
   const long long abs_ = static_cast<long long>(dims->audio_seq) * dims->audio_dim;
   if ((rc = pack_embed_weights(dims, w, ws, st))) return rc;
+  if ((rc = zero_ln_sync(ws, st))) return rc;
   if ((rc = run_trunk(dims, w, motion, mbs, audio, abs_, nullptr, batch, mode, ws, false, st))) return rc;
   // output Dense on all 360 rows (base_models.py:200)
   const int d = dims->d_model, ns = dims->motion_seq + dims->audio_seq, M = batch * ns;
@@ -516,8 +536,9 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
   FACT_REQUIRE(dims->out_dim == dims->motion_dim, FACT_ERR_BAD_SHAPE,
                "AR feedback needs out_dim == motion feature dim (fact_model.py:131)");
   {  // outside the per-frame graph: the embedding kernels may have changed since the last call
-    const int rc = pack_embed_weights(dims, w, ws, st);
+    int rc = pack_embed_weights(dims, w, ws, st);
     if (rc) return rc;
+    if ((rc = zero_ln_sync(ws, st))) return rc;
   }
 
   auto one_frame = [&](cudaStream_t s) -> int {
@@ -560,7 +581,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
   FACT_CUDA_CHECK(cudaGetDevice(&device));
   key.add(static_cast<uintptr_t>(device));
   for (int f : {g_ar_prune, g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_dual_stream, g_gemm_tma_store, g_gemm_bn,
-                g_gemm_finish_ln, g_ar_fused, g_pdl})   // g_pdl stays LAST: the capture fallback below rewrites it
+                g_gemm_finish_ln, g_ar_fused, g_sdpa_wide, g_gemm_fuse_ln, g_pdl})   // g_pdl stays LAST: the capture fallback below rewrites it
     key.add(static_cast<uintptr_t>(f));
   ArSession* sess = session ? static_cast<ArSession*>(session) : &g_default_session;
   cudaGraphExec_t exec = nullptr;

@@ -57,6 +57,8 @@ struct TrainWs {
   // LinearEmbedding on the tensor path: bf16 inputs [tokens, kp] (kept for the weight gradient), kernels [d, kp]
   bf16 *em_x, *ea_x, *em_w, *ea_w;
   int em_kp, ea_kp;
+  int* ln_sync;  // arrival counters of the residual GEMMs that normalise their own rows (fact_gemm_epilogue.ln_sync)
+  size_t ln_sync_bytes;
 };
 
 static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
@@ -117,6 +119,8 @@ static size_t carve_train(const fact_dims* dm, int batch, void* base, TrainWs* w
   w.ea_x = reinterpret_cast<bf16*>(take(Ma * w.ea_kp * 2));
   w.em_w = reinterpret_cast<bf16*>(take(d * w.em_kp * 2));
   w.ea_w = reinterpret_cast<bf16*>(take(d * w.ea_kp * 2));
+  w.ln_sync_bytes = ((Mc + 31) / 32 + 1) * sizeof(int);
+  w.ln_sync = reinterpret_cast<int*>(take(w.ln_sync_bytes));
   if (ws) *ws = w;
   return off;
 }
@@ -154,11 +158,16 @@ static int embed_bwd_train(const bf16* x_b, int kp, const float* dy, const bf16*
 }
 
 // forward of one layer, saving what the backward needs; `out` = where the layer's output residual stream goes
+// ln1_done: S.ln1 already holds LayerNorm1(S.x_in) (the FF2 call of the layer below produced it); next / next_ln1: the
+// layer above in the same stack, whose LayerNorm1 this layer's FF2 call produces (NULL: nobody, or the output is
+// remapped into the concatenated buffer).  The LayerNorms ride on the residual GEMM calls (fact_gemm_epilogue.ln_*):
+// at training batch sizes the GEMM's own LayerNorm warps write them inside the launch.
 static int layer_fwd_train(const fact_dims* dm, const fact_layer_weights& L, const SavedLayer& S, int batch, int seq,
-                           float* out, int out_seq, int out_off, cudaStream_t st) {
+                           float* out, int out_seq, int out_off, bool ln1_done, const fact_layer_weights* next,
+                           bf16* next_ln1, int* ln_sync, cudaStream_t st) {
   const int d = dm->d_model, ff = dm->d_ff, H = dm->n_heads, dh = d / H, M = batch * seq;
   int rc;
-  if ((rc = fact_layernorm_split(S.x_in, L.ln1_gamma, L.ln1_beta, S.ln1, nullptr, M, d, st))) return rc;
+  if (!ln1_done && (rc = fact_layernorm_split(S.x_in, L.ln1_gamma, L.ln1_beta, S.ln1, nullptr, M, d, st))) return rc;
   fact_gemm_epilogue e{};
   e.kind = FACT_EPI_SPLIT;
   e.out_hi = S.qkv;
@@ -174,8 +183,11 @@ static int layer_fwd_train(const fact_dims* dm, const fact_layer_weights& L, con
   e.bias = L.bo;
   e.resid = S.x_in;
   e.ldr = d;
+  e.ln_gamma = L.ln2_gamma;  // LayerNorm2 of the rows this call writes
+  e.ln_beta = L.ln2_beta;
+  e.ln_hi = S.ln2;
+  e.ln_sync = ln_sync;
   if ((rc = bf16_gemm(S.ao, d, L.wo_hi, d, M, d, d, &e, st))) return rc;
-  if ((rc = fact_layernorm_split(S.x_mid, L.ln2_gamma, L.ln2_beta, S.ln2, nullptr, M, d, st))) return rc;
   e = fact_gemm_epilogue{};
   e.kind = FACT_EPI_BIAS_GELU_SAVE;
   e.out_hi = S.h;
@@ -194,6 +206,11 @@ static int layer_fwd_train(const fact_dims* dm, const fact_layer_weights& L, con
     e.seq_in = seq;
     e.seq_out = out_seq;
     e.seq_off = out_off;
+  } else if (next) {  // LayerNorm1 of the layer above
+    e.ln_gamma = next->ln1_gamma;
+    e.ln_beta = next->ln1_beta;
+    e.ln_hi = next_ln1;
+    e.ln_sync = ln_sync;
   }
   return bf16_gemm(S.h, ff, L.w2_hi, ff, M, d, ff, &e, st);
 }
@@ -294,6 +311,7 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
     return FACT_OK;
   };
 
+  FACT_CUDA_CHECK(cudaMemsetAsync(ws.ln_sync, 0, ws.ln_sync_bytes, st));
   // ------------------------------------------------------------------ forward (saves activations)
   if ((rc = embed_fwd_train(motion, w->motion_embed_w, w->motion_embed_b, w->motion_pos, Sm[0].x_in, ws.em_x, ws.em_w,
                             ws.em_kp, batch, dims->motion_seq, dims->motion_dim, d, st)))
@@ -301,7 +319,8 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   for (int l = 0; l < dims->motion_layers; ++l) {
     const bool last = l + 1 == dims->motion_layers;
     if ((rc = layer_fwd_train(dims, w->motion_layers[l], Sm[l], batch, dims->motion_seq,
-                              last ? Sc[0].x_in : Sm[l + 1].x_in, last ? ns : 0, 0, st)))
+                              last ? Sc[0].x_in : Sm[l + 1].x_in, last ? ns : 0, 0, l > 0,
+                              last ? nullptr : &w->motion_layers[l + 1], last ? nullptr : Sm[l + 1].ln1, ws.ln_sync, st)))
       return rc;
   }
   if ((rc = embed_fwd_train(audio, w->audio_embed_w, w->audio_embed_b, w->audio_pos, Sa[0].x_in, ws.ea_x, ws.ea_w,
@@ -310,12 +329,14 @@ extern "C" int fact_train_step(const fact_dims* dims, const fact_weights* w, con
   for (int l = 0; l < dims->audio_layers; ++l) {
     const bool last = l + 1 == dims->audio_layers;
     if ((rc = layer_fwd_train(dims, w->audio_layers[l], Sa[l], batch, dims->audio_seq,
-                              last ? Sc[0].x_in : Sa[l + 1].x_in, last ? ns : 0, last ? dims->motion_seq : 0, st)))
+                              last ? Sc[0].x_in : Sa[l + 1].x_in, last ? ns : 0, last ? dims->motion_seq : 0, l > 0,
+                              last ? nullptr : &w->audio_layers[l + 1], last ? nullptr : Sa[l + 1].ln1, ws.ln_sync, st)))
       return rc;
   }
   for (int l = 0; l < dims->cross_layers; ++l) {
     const bool last = l + 1 == dims->cross_layers;
-    if ((rc = layer_fwd_train(dims, w->cross_layers[l], Sc[l], batch, ns, last ? ws.xf : Sc[l + 1].x_in, 0, 0, st)))
+    if ((rc = layer_fwd_train(dims, w->cross_layers[l], Sc[l], batch, ns, last ? ws.xf : Sc[l + 1].x_in, 0, 0, l > 0,
+                              last ? nullptr : &w->cross_layers[l + 1], last ? nullptr : Sc[l + 1].ln1, ws.ln_sync, st)))
       return rc;
   }
   if ((rc = fact_layernorm_split(ws.xf, nullptr, nullptr, ws.xf_b, nullptr, Mc, d, st))) return rc;

@@ -387,6 +387,76 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ----------------------------------------------------------------------------- LayerNorm of one row by one warp
+// Norm (mint/core/base_models.py:22-31): eps 1e-5, biased variance, two passes over the row held in registers
+// (d <= 1024, d % 4 == 0), result split into bf16 hi (+ lo).  Shared by ln_split_kernel and the LayerNorm warps of the
+// CTA-pair GEMM so that both produce the same bits.  CG: read x through the L2 only (rows other SMs have just written).
+template <bool CG>
+__device__ __forceinline__ void ln_row_load(const float* __restrict__ xrow, int nv, int lane, float4* v) {
+  const float4* xr = reinterpret_cast<const float4*>(xrow);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    v[i] = idx < nv ? (CG ? __ldcg(xr + idx) : __ldg(xr + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <bool NORM>
+__device__ __forceinline__ void ln_row_finish(const float4* v, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta, bf16* __restrict__ hi_row,
+                                              bf16* __restrict__ lo_row, int d, int lane) {
+  const int nv = d >> 2;
+  float mean = 0.f, rstd = 1.f;
+  if (NORM) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / static_cast<float>(d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + i * 32 < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q / static_cast<float>(d) + 1e-5f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* hr = reinterpret_cast<uint2*>(hi_row);
+  uint2* lr = lo_row ? reinterpret_cast<uint2*>(lo_row) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      float4 y = v[i];
+      if (NORM) {
+        const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
+        y.x = (y.x - mean) * rstd * gg.x + bb.x;
+        y.y = (y.y - mean) * rstd * gg.y + bb.y;
+        y.z = (y.z - mean) * rstd * gg.z + bb.z;
+        y.w = (y.w - mean) * rstd * gg.w + bb.w;
+      }
+      bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(y.x, h0, l0);
+      split_bf16(y.y, h1, l1);
+      split_bf16(y.z, h2, l2);
+      split_bf16(y.w, h3, l3);
+      hr[idx] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      if (lr) lr[idx] = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+  }
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),

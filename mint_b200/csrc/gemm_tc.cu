@@ -49,6 +49,7 @@ struct EpiArgs {
   const float* ln_beta;
   bf16* ln_hi;
   bf16* ln_lo;
+  int* ln_sync;  // pair kernel with LayerNorm warps: arrival counters, one per 32-row group (zero between launches)
 };
 
 template <int BN, int NPART, int STAGES>
@@ -791,8 +792,16 @@ __device__ __forceinline__ void epilogue_compute(const float* v, int row, int co
   }
 }
 
-template <int BN, int NPART, int STAGES, int EPI, bool TS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_tc2_kernel(
+// LNW (BIAS_RESID_F32 through the bulk-store epilogue only): four more warps per CTA normalise the finished rows.
+// A residual-stream row is complete when the tiles_n column tiles of its 256-row block have all landed, and those are
+// handled by tiles_n different clusters: every epilogue warp counts its 32-row group in ep.ln_sync once its bulk stores
+// / reductions of a tile have completed, and the LayerNorm warps of the CTA that owns column tile 0 wait for the count
+// (2 warps x tiles_n), then read the rows back from the L2 and write LayerNorm(row) split into bf16 hi / lo -- the A
+// operand of the next GEMM -- while the MMA and epilogue warps are already on their next tiles.  Same arithmetic as
+// ln_split_kernel (ln_row_finish), which this replaces: one launch and one HBM read of the residual stream fewer.
+constexpr int LN_WARPS = 4;
+template <int BN, int NPART, int STAGES, int EPI, bool TS, bool LNW = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS + (LNW ? LN_WARPS * 32 : 0), 1) gemm_tc2_kernel(
     const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, int M, int N, int K,
@@ -908,8 +917,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         }
       }
     }
+  } else if (LNW && warp >= 2 + EPI_WARPS) {  // ---------------- LayerNorm warps (both CTAs)
+    const int j = warp - (2 + EPI_WARPS);  // 32-row group inside this CTA's 128 rows
+    const int target = 2 * tiles_n;        // two epilogue warps (column halves) per column tile
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      if (tile % tiles_n != 0) continue;   // the cluster that has column tile 0 normalises the block's rows
+      const int row0 = (tile / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + j * 32;
+      if (row0 >= M) continue;
+      int* ctr = ep.ln_sync + (row0 >> 5);
+      if (lane == 0) {
+        // bounded: a GEMM launch lasts about a millisecond; a count that has not arrived after ~a second never will
+        // (a caller that handed in dirty counters, or two streams sharing them) -> fail the launch instead of hanging
+        unsigned spins = 0;
+        while (ld_acquire_gpu(ctr) < target) {
+          __nanosleep(200);
+          if (++spins > (1u << 22)) __trap();
+        }
+        *ctr = 0;  // nobody touches the counter again before the next launch
+      }
+      __syncwarp();
+      const int nrows = min(32, M - row0), nv = N >> 2;
+      for (int r = 0; r < nrows; r += 2) {  // two rows in flight: the loads come from the L2
+        float4 v0[8], v1[8];
+        const int ra = row0 + r, rb = row0 + r + 1;
+        const bool second = r + 1 < nrows;
+        ln_row_load<true>(ep.out_f32 + static_cast<size_t>(ra) * ep.ldo, nv, lane, v0);
+        if (second) ln_row_load<true>(ep.out_f32 + static_cast<size_t>(rb) * ep.ldo, nv, lane, v1);
+        ln_row_finish<true>(v0, ep.ln_gamma, ep.ln_beta, ep.ln_hi + static_cast<size_t>(ra) * N,
+                            ep.ln_lo ? ep.ln_lo + static_cast<size_t>(ra) * N : nullptr, N, lane);
+        if (second)
+          ln_row_finish<true>(v1, ep.ln_gamma, ep.ln_beta, ep.ln_hi + static_cast<size_t>(rb) * N,
+                              ep.ln_lo ? ep.ln_lo + static_cast<size_t>(rb) * N : nullptr, N, lane);
+      }
+    }
   } else if (TS) {  // ---------------- epilogue warps, bulk-store flavour: stage a 32 x 32 box, one TMA store per box
     const int q = warp & 3, half = (warp - 2) >> 2;
+    int ln_pending = -1;  // LNW: 32-row group whose stores of the previous tile are not yet counted in ep.ln_sync
     const uint32_t stg = staging_base + static_cast<uint32_t>(warp - 2) * TS_WARP_BYTES;
     constexpr bool F32_OUT = EPI == FACT_EPI_BIAS_RESID_F32 || EPI == FACT_EPI_BIAS_F32;
     const bool two = !F32_OUT && ep.out_lo != nullptr;
@@ -921,6 +964,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       const bool row_ok = row < M;
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
+      if (LNW && ln_pending >= 0) {
+        // the previous tile's boxes were issued a whole main loop ago: by now this wait is free.  Completed bulk
+        // stores / reductions + gpu-scope fence + atomic = the rows are visible to whoever reads the full count.
+        if (lane == 0) {
+          bulk_wait_group0();
+          __threadfence();
+          atomicAdd(ep.ln_sync + (ln_pending >> 5), 1);
+        }
+        ln_pending = -1;
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n0 + c * 32;
@@ -977,8 +1030,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         if (leader) mbar_arrive(tmem_empty_bar(acc));
         else mbar_arrive_leader(tmem_empty_bar(acc));
       }
+      if (LNW && row0 < M) ln_pending = row0;
     }
     if (lane == 0) bulk_wait_group0();  // all boxes written before the CTA (and its shared memory) goes away
+    if (LNW && ln_pending >= 0 && lane == 0) {
+      __threadfence();
+      atomicAdd(ep.ln_sync + (ln_pending >> 5), 1);
+    }
   } else {  // ---------------- epilogue warps (both CTAs): this CTA's 128 rows of the pair tile
     const int q = warp & 3, half = (warp - 2) >> 2;
     uint32_t t = 0;
@@ -1219,11 +1277,11 @@ struct OutMaps {
   CUtensorMap o0, o1;
 };
 
-template <int BN, int NPART, int STAGES, int EPI, bool TS>
+template <int BN, int NPART, int STAGES, int EPI, bool TS, bool LNW = false>
 static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                        const OutMaps& om, int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN, NPART, STAGES, TS>;
-  auto kern = gemm_tc2_kernel<BN, NPART, STAGES, EPI, TS>;
+  auto kern = gemm_tc2_kernel<BN, NPART, STAGES, EPI, TS, LNW>;
   static bool attr_done = false;
   if (!attr_done) {
     FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1233,8 +1291,8 @@ static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   const int num_tiles = tiles_n * tiles_m;
   int clusters = num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  FACT_CUDA_CHECK(launch_k(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, true, a0, a1, b0, b1, om.o0,
-                           om.o1, m, n, k, tiles_n, num_tiles, ep));
+  FACT_CUDA_CHECK(launch_k(kern, dim3(2 * clusters), dim3(GEMM_THREADS + (LNW ? LN_WARPS * 32 : 0)), Cfg::SMEM_BYTES, st,
+                           true, a0, a1, b0, b1, om.o0, om.o1, m, n, k, tiles_n, num_tiles, ep));
   FACT_LAUNCH_CHECK("gemm_tc2_kernel launch");
   return FACT_OK;
 }
@@ -1297,6 +1355,7 @@ int gemm_tile_n(int n) {
 
 int g_gemm_tma_store = 1;  // fact_set_flag("gemm_tma_store", 0 | 1 | 2): pair-kernel epilogue through bulk tensor stores
                            // (0 = direct row-per-lane stores, 2 = bulk stores but no in-place bulk reduction)
+int g_gemm_fuse_ln = 1;    // fact_set_flag("gemm_fuse_ln", 0): large batches keep the LayerNorm as its own launch
 int g_gemm_finish_ln = 1;  // fact_set_flag("gemm_finish_ln", 0): keep the LayerNorm out of the split-K finish kernel
                            // (batch 1: 722 frames/s fused, block per row, vs 656 with a separate LayerNorm launch)
 int g_pdl = 1;          // fact_set_flag("pdl", 0): plain serialized launches for the small-batch decode chain
@@ -1374,6 +1433,7 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
   ep.ln_beta = nullptr;
   ep.ln_hi = nullptr;
   ep.ln_lo = nullptr;
+  ep.ln_sync = nullptr;
   if (split_out)
     ep.vec_ok = (ep.ldo % 8 == 0) && aligned16(ep.out_hi) && (!ep.out_lo || aligned16(ep.out_lo)) &&
                 (!ep.bias || aligned16(ep.bias)) && (!ep.aux || (aligned16(ep.aux) && ep.ldaux % 8 == 0));
@@ -1454,6 +1514,20 @@ static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void
       }
       if ((rc = make_tmap_out(&om.o0, out0, m, n, ep.ldo, esz))) return rc;
       if (split_out && ep.out_lo && (rc = make_tmap_out(&om.o1, ep.out_lo, m, n, ep.ldo, 2))) return rc;
+      // LayerNorm of the finished rows inside this launch (dedicated warps) instead of a launch after it
+      if (epi->ln_hi && epi->ln_sync && g_gemm_fuse_ln && epi->kind == FACT_EPI_BIAS_RESID_F32 && bn == 160 &&
+          n % 160 == 0 && aligned16(epi->ln_gamma) && aligned16(epi->ln_beta) &&
+          (reinterpret_cast<uintptr_t>(epi->ln_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(epi->ln_lo) & 7) == 0) {
+        ep.ln_gamma = epi->ln_gamma;
+        ep.ln_beta = epi->ln_beta;
+        ep.ln_hi = static_cast<bf16*>(epi->ln_hi);
+        ep.ln_lo = static_cast<bf16*>(epi->ln_lo);
+        ep.ln_sync = epi->ln_sync;
+        *colsum_fused = true;
+        if (precise)
+          return launch_cfg2<160, 2, 3, FACT_EPI_BIAS_RESID_F32, true, true>(a0, a1, b0, b1, om, m, n, k, ep, st);
+        return launch_cfg2<160, 1, 7, FACT_EPI_BIAS_RESID_F32, true, true>(a0, a1, b0, b1, om, m, n, k, ep, st);
+      }
       if (precise) {
         if (bn == 160) return launch_epi2<160, 2, 3, true>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);
         return launch_epi2<256, 2, 3, true>(epi->kind, a0, a1, b0, b1, om, m, n, k, ep, st);

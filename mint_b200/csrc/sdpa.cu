@@ -275,6 +275,8 @@ extern int g_sdpa_bwd_tc;
 extern int g_dual_stream;
 extern int g_ar_prune;
 extern int g_ar_fused;
+extern int g_sdpa_wide;
+extern int g_gemm_fuse_ln;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
 
 }  // namespace fact
@@ -293,7 +295,8 @@ extern "C" int fact_set_flag(const char* name, int value) {
                         {"sdpa_bwd_tc", &g_sdpa_bwd_tc},   {"gemm_finish_ln", &g_gemm_finish_ln},
                         {"wgrad_pair", &g_wgrad_pair},     {"gemm_tma_store", &g_gemm_tma_store},
                         {"gemm_splitk", &g_gemm_splitk},   {"gemm_pair", &g_gemm_pair},
-                        {"ar_fused", &g_ar_fused},         {"pdl", &g_pdl}};
+                        {"ar_fused", &g_ar_fused},         {"pdl", &g_pdl},
+                        {"sdpa_wide", &g_sdpa_wide},       {"gemm_fuse_ln", &g_gemm_fuse_ln}};
   for (const Flag& f : flags)
     if (name && strcmp(name, f.name) == 0) {
       *f.slot = value;

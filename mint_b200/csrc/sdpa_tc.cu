@@ -8,8 +8,12 @@
 //     mode each product is hi.hi + lo.hi + hi.lo accumulated in the same TMEM tile;
 //   * P is written back IN PLACE over S (32 fp32 columns -> 16 columns bf16 P_hi | 16 columns bf16 P_lo) with
 //     tcgen05.st and consumed by the PV MMA as a TMEM A-operand -- probabilities never touch shared or global memory;
-//   * Q/K/V head slices arrive by TMA as [rows][16]-element sub-tiles (SWIZZLE_32B; 80 = 5 x 16 so no padding);
-//     K sub-tiles are K-major B operands, V sub-tiles are MN-major B operands of the PV product;
+//   * Q/K/V head slices arrive by TMA.  WIDE = 0: five [rows][16]-element sub-tiles per operand part (SWIZZLE_32B;
+//     80 = 5 x 16 so no padding); K sub-tiles are K-major B operands, V sub-tiles MN-major B operands of the PV product.
+//     WIDE >= 1: a Q / K part is ONE [rows][64] box (SWIZZLE_128B, 128-byte rows: a quarter of the TMA row requests and
+//     conflict-free operand reads) + one [rows][16] box (SWIZZLE_32B) for head dims 64..79 -- four K steps read the wide
+//     box, the fifth the narrow one.  WIDE = 2: V the same way; the PV product becomes an N = 64 MMA (MN-major
+//     SWIZZLE_128B) plus an N = 16 MMA into adjacent TMEM columns;
 //   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = softmax + output (TMEM lane quadrant = warp % 4, two
 //     warps per quadrant split the score columns and exchange row max / sum through shared memory).
 // Keys beyond N inside the last 128-key block are other rows of the qkv buffer (or TMA zero fill): their scores are
@@ -41,9 +45,12 @@ struct SdpaTcCfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
-template <int NPART>
+constexpr int TC_WIDE_BYTES = TC_KB * 128;  // the [128 rows][64 el] SWIZZLE_128B box of a wide operand part (16 KB)
+
+template <int NPART, int WIDE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
                bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, float* __restrict__ lse, int N, int H, int q_blocks,
                int num_tiles) {
   using Cfg = SdpaTcCfg<NPART>;
@@ -73,6 +80,10 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_hi);
     if (NPART == 2) tma_prefetch_desc(&tm_lo);
+    if (WIDE > 0) {
+      tma_prefetch_desc(&tw_hi);
+      if (NPART == 2) tma_prefetch_desc(&tw_lo);
+    }
     for (int s = 0; s < TC_KV_STAGES; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
@@ -105,13 +116,22 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   if (warp == 0) {
     {  // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
       uint32_t it = 0, t = 0;
-      auto load_block = [&](uint32_t dst, uint32_t bar, int col, int row) {
+      auto load_block = [&](uint32_t dst, uint32_t bar, int col, int row, bool wide) {
         if (elect_one()) {
           mbar_arrive_expect_tx(bar, Cfg::TILE_BYTES);
+          if (wide) {  // [rows][64] SWIZZLE_128B box + [rows][16] SWIZZLE_32B box per part (same 20 KB)
+            tma_load_2d(dst, &tw_hi, col, row, bar);
+            tma_load_2d(dst + TC_WIDE_BYTES, &tm_hi, col + 64, row, bar);
+            if (NPART == 2) {
+              tma_load_2d(dst + Cfg::PART_BYTES, &tw_lo, col, row, bar);
+              tma_load_2d(dst + Cfg::PART_BYTES + TC_WIDE_BYTES, &tm_lo, col + 64, row, bar);
+            }
+          } else {
 #pragma unroll
-          for (int ks = 0; ks < TC_KS; ++ks) {
-            tma_load_2d(dst + ks * TC_SUB, &tm_hi, col + ks * 16, row, bar);
-            if (NPART == 2) tma_load_2d(dst + Cfg::PART_BYTES + ks * TC_SUB, &tm_lo, col + ks * 16, row, bar);
+            for (int ks = 0; ks < TC_KS; ++ks) {
+              tma_load_2d(dst + ks * TC_SUB, &tm_hi, col + ks * 16, row, bar);
+              if (NPART == 2) tma_load_2d(dst + Cfg::PART_BYTES + ks * TC_SUB, &tm_lo, col + ks * 16, row, bar);
+            }
           }
         }
         __syncwarp();
@@ -121,12 +141,12 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         tile_coords(tile, b, h, qb);
         const int row0 = b * N;
         mbar_wait(q_empty, (t & 1) ^ 1);
-        load_block(q_smem, q_full, h * TC_DH, row0 + qb * TC_QB);
+        load_block(q_smem, q_full, h * TC_DH, row0 + qb * TC_QB, WIDE >= 1);
         for (int which = 1; which <= 2; ++which)      // all K blocks, then all V blocks
           for (int c = 0; c < nblk; ++c, ++it) {
             const int s = it % TC_KV_STAGES;
             mbar_wait(kv_empty(s), ((it / TC_KV_STAGES) & 1) ^ 1);
-            load_block(kv_smem(s), kv_full(s), which * D + h * TC_DH, row0 + c * TC_KB);
+            load_block(kv_smem(s), kv_full(s), which * D + h * TC_DH, row0 + c * TC_KB, WIDE >= which);
           }
       }
     }
@@ -134,6 +154,8 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     {  // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32_ex(TC_QB, TC_KB, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16_f32_ex(TC_QB, TC_DH, 1);
+      constexpr uint32_t idesc_o64 = umma_idesc_bf16_f32_ex(TC_QB, 64, 1);
+      constexpr uint32_t idesc_o16 = umma_idesc_bf16_f32_ex(TC_QB, 16, 1);
       uint32_t it = 0, t = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t tph = t & 1;
@@ -146,16 +168,25 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           tc_fence_after();
           const uint32_t d = tmem_base + c * TC_KB;
           if (elect_one()) {
-            const uint64_t qh0 = umma_desc_k_sw32(q_smem), kh0 = umma_desc_k_sw32(kv_smem(s));
-            const uint64_t ql0 = umma_desc_k_sw32(q_smem + (NPART - 1) * Cfg::PART_BYTES);
-            const uint64_t kl0 = umma_desc_k_sw32(kv_smem(s) + (NPART - 1) * Cfg::PART_BYTES);
+            const uint32_t ql_s = q_smem + (NPART - 1) * Cfg::PART_BYTES;
+            const uint32_t kh_s = kv_smem(s), kl_s = kv_smem(s) + (NPART - 1) * Cfg::PART_BYTES;
+            // WIDE: K steps 0..3 walk the 128-byte rows of the wide box (32 bytes per step), step 4 is the narrow box
+            const uint64_t qh0 = WIDE ? umma_desc_k_sw128(q_smem) : umma_desc_k_sw32(q_smem);
+            const uint64_t kh0 = WIDE ? umma_desc_k_sw128(kh_s) : umma_desc_k_sw32(kh_s);
+            const uint64_t ql0 = WIDE ? umma_desc_k_sw128(ql_s) : umma_desc_k_sw32(ql_s);
+            const uint64_t kl0 = WIDE ? umma_desc_k_sw128(kl_s) : umma_desc_k_sw32(kl_s);
+            const uint64_t qh4 = umma_desc_k_sw32(q_smem + TC_WIDE_BYTES), kh4 = umma_desc_k_sw32(kh_s + TC_WIDE_BYTES);
+            const uint64_t ql4 = umma_desc_k_sw32(ql_s + TC_WIDE_BYTES), kl4 = umma_desc_k_sw32(kl_s + TC_WIDE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < TC_KS; ++ks) {
-              const uint64_t off = static_cast<uint64_t>(ks * TC_SUB) >> 4;
-              umma_bf16(d, qh0 + off, kh0 + off, idesc_s, ks > 0 ? 1u : 0u);
+              const uint64_t off = WIDE ? static_cast<uint64_t>(ks * 32) >> 4 : static_cast<uint64_t>(ks * TC_SUB) >> 4;
+              const bool tail = WIDE && ks == TC_KS - 1;
+              const uint64_t aqh = tail ? qh4 : qh0 + off, akh = tail ? kh4 : kh0 + off;
+              const uint64_t aql = tail ? ql4 : ql0 + off, akl = tail ? kl4 : kl0 + off;
+              umma_bf16(d, aqh, akh, idesc_s, ks > 0 ? 1u : 0u);
               if (NPART == 2) {
-                umma_bf16(d, ql0 + off, kh0 + off, idesc_s, 1u);
-                umma_bf16(d, qh0 + off, kl0 + off, idesc_s, 1u);
+                umma_bf16(d, aql, akh, idesc_s, 1u);
+                umma_bf16(d, aqh, akl, idesc_s, 1u);
               }
             }
             umma_commit(kv_empty(s));
@@ -174,17 +205,43 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           const int nvalid = min(TC_KB, N - c * TC_KB);
           const int ksteps = (nvalid + 15) >> 4;
           if (elect_one()) {
-            const uint64_t vh0 = umma_desc_mn_sw32(kv_smem(s), TC_SUB, 256);
-            const uint64_t vl0 = umma_desc_mn_sw32(kv_smem(s) + (NPART - 1) * Cfg::PART_BYTES, TC_SUB, 256);
+            const uint32_t vh_s = kv_smem(s), vl_s = kv_smem(s) + (NPART - 1) * Cfg::PART_BYTES;
+            if (WIDE == 2) {
+              // head dims 0..63: one MN-major SWIZZLE_128B atom (16 keys = two 8-row groups = 2048 bytes per step);
+              // head dims 64..79: the narrow SWIZZLE_32B box (512 bytes per step); O columns 0..63 and 64..79
+              const uint64_t vh0 = umma_desc_mn_sw128(vh_s, TC_WIDE_BYTES, 1024);
+              const uint64_t vl0 = umma_desc_mn_sw128(vl_s, TC_WIDE_BYTES, 1024);
+              const uint64_t th0 = umma_desc_mn_sw32(vh_s + TC_WIDE_BYTES, TC_SUB, 256);
+              const uint64_t tl0 = umma_desc_mn_sw32(vl_s + TC_WIDE_BYTES, TC_SUB, 256);
 #pragma unroll
-            for (int j = 0; j < TC_KB / 16; ++j) {
-              if (j < ksteps) {
-                const uint32_t a_hi = tmem_base + c * TC_KB + 32 * (j >> 1) + 8 * (j & 1);
-                const uint64_t off = static_cast<uint64_t>(j * 512) >> 4;
-                umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vh0 + off, idesc_o, (c > 0 || j > 0) ? 1u : 0u);
-                if (NPART == 2) {
-                  umma_bf16_ts(tmem_base + TC_O_COL, a_hi + 16, vh0 + off, idesc_o, 1u);
-                  umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vl0 + off, idesc_o, 1u);
+              for (int j = 0; j < TC_KB / 16; ++j) {
+                if (j < ksteps) {
+                  const uint32_t a_hi = tmem_base + c * TC_KB + 32 * (j >> 1) + 8 * (j & 1);
+                  const uint64_t offw = static_cast<uint64_t>(j * 2048) >> 4, offt = static_cast<uint64_t>(j * 512) >> 4;
+                  const uint32_t accf = (c > 0 || j > 0) ? 1u : 0u;
+                  umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vh0 + offw, idesc_o64, accf);
+                  umma_bf16_ts(tmem_base + TC_O_COL + 64, a_hi, th0 + offt, idesc_o16, accf);
+                  if (NPART == 2) {
+                    umma_bf16_ts(tmem_base + TC_O_COL, a_hi + 16, vh0 + offw, idesc_o64, 1u);
+                    umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vl0 + offw, idesc_o64, 1u);
+                    umma_bf16_ts(tmem_base + TC_O_COL + 64, a_hi + 16, th0 + offt, idesc_o16, 1u);
+                    umma_bf16_ts(tmem_base + TC_O_COL + 64, a_hi, tl0 + offt, idesc_o16, 1u);
+                  }
+                }
+              }
+            } else {
+              const uint64_t vh0 = umma_desc_mn_sw32(vh_s, TC_SUB, 256);
+              const uint64_t vl0 = umma_desc_mn_sw32(vl_s, TC_SUB, 256);
+#pragma unroll
+              for (int j = 0; j < TC_KB / 16; ++j) {
+                if (j < ksteps) {
+                  const uint32_t a_hi = tmem_base + c * TC_KB + 32 * (j >> 1) + 8 * (j & 1);
+                  const uint64_t off = static_cast<uint64_t>(j * 512) >> 4;
+                  umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vh0 + off, idesc_o, (c > 0 || j > 0) ? 1u : 0u);
+                  if (NPART == 2) {
+                    umma_bf16_ts(tmem_base + TC_O_COL, a_hi + 16, vh0 + off, idesc_o, 1u);
+                    umma_bf16_ts(tmem_base + TC_O_COL, a_hi, vl0 + off, idesc_o, 1u);
+                  }
                 }
               }
             }
@@ -312,18 +369,22 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   }
 }
 
-template <int NPART>
+// fact_set_flag("sdpa_wide", v): 0 = five 16-column SWIZZLE_32B sub-tiles per operand part, 1 = Q / K as a 64-column
+// SWIZZLE_128B box + a 16-column box, 2 = V as well (PV split into an N = 64 and an N = 16 MMA)
+int g_sdpa_wide = 1;
+
+template <int NPART, int WIDE>
 static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, int batch, int n,
                           int heads, int q_rows, cudaStream_t st) {
   using Cfg = SdpaTcCfg<NPART>;
-  auto kern = sdpa_tc_kernel<NPART>;
-  static bool attr_done = false;
+  auto kern = sdpa_tc_kernel<NPART, WIDE>;
+  static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   const int d = heads * TC_DH;
-  CUtensorMap tmh, tml;
+  CUtensorMap tmh, tml, twh, twl;
   int rc;
   if ((rc = make_tmap_bf16(&tmh, qh, batch * n, 3 * d, 3 * d, TC_KB, 16))) return rc;
   if (NPART == 2) {
@@ -331,11 +392,18 @@ static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, fl
   } else {
     tml = tmh;
   }
+  twh = tmh;
+  twl = tml;
+  if (WIDE > 0) {
+    if ((rc = make_tmap_bf16(&twh, qh, batch * n, 3 * d, 3 * d, TC_KB, 64))) return rc;
+    twl = twh;
+    if (NPART == 2 && (rc = make_tmap_bf16(&twl, ql, batch * n, 3 * d, 3 * d, TC_KB, 64))) return rc;
+  }
   const int q_blocks = (q_rows + TC_QB - 1) / TC_QB;
   const int num_tiles = q_blocks * heads * batch;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  FACT_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, true, tmh, tml, oh, ol, lse, n, heads,
-                           q_blocks, num_tiles));
+  FACT_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, true, tmh, tml, twh, twl, oh, ol, lse,
+                           n, heads, q_blocks, num_tiles));
   FACT_LAUNCH_CHECK("sdpa_tc_kernel launch");
   return FACT_OK;
 }
@@ -348,8 +416,13 @@ int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, 
   if ((reinterpret_cast<uintptr_t>(qh) | reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ql) |
        reinterpret_cast<uintptr_t>(ol)) & 15)
     return FACT_ERR_UNSUPPORTED;
-  return ql ? launch_sdpa_tc<2>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)
-            : launch_sdpa_tc<1>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st);
+#define FACT_SDPA_TC(W)                                                                   \
+  return ql ? launch_sdpa_tc<2, W>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)      \
+            : launch_sdpa_tc<1, W>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)
+  if (g_sdpa_wide == 2) { FACT_SDPA_TC(2); }
+  if (g_sdpa_wide == 1) { FACT_SDPA_TC(1); }
+  FACT_SDPA_TC(0);
+#undef FACT_SDPA_TC
 }
 
 }  // namespace fact

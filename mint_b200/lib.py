@@ -50,7 +50,7 @@ class Grads(C.Structure):
         "out_w", "out_b")]
 
 
-ABI_VERSION = 3  # FACT_ABI_VERSION of include/fact_sm100.h these ctypes declarations mirror
+ABI_VERSION = 4  # FACT_ABI_VERSION of include/fact_sm100.h these ctypes declarations mirror
 
 
 class GemmEpilogue(C.Structure):
@@ -58,7 +58,7 @@ class GemmEpilogue(C.Structure):
                 ("resid", _vp), ("ldr", _i), ("scale", _f), ("scale_cols", _i), ("seq_in", _i), ("seq_out", _i),
                 ("seq_off", _i), ("aux", _vp), ("ldaux", _i), ("splitk_scratch", _vp), ("splitk_scratch_bytes", C.c_size_t),
                 ("colsum", _vp), ("resid_rows", _i),
-                ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_hi", _vp), ("ln_lo", _vp)]
+                ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_hi", _vp), ("ln_lo", _vp), ("ln_sync", _vp)]
 
 
 # symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/fact_sm100.h

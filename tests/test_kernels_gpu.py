@@ -337,6 +337,58 @@ def test_gemm_residual_with_layernorm(fact_lib, cuda, m, n, k, pitch_rows, preci
     assert rel_err(got, ln_ref) < (3e-5 if precise else 4e-3)
 
 
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("inplace", [True, False])
+@pytest.mark.parametrize("m,k", [(46080 // 4, 800), (20000, 3072), (19999, 800)])
+def test_gemm_layernorm_inside_the_launch(fact_lib, cuda, m, k, inplace, precise):
+    """CTA-pair GEMM whose LayerNorm warps normalise the finished rows inside the launch (ln_sync given, flag
+    gemm_fuse_ln = 1): bit-identical to the same GEMM followed by the LayerNorm launch (flag 0), for the in-place
+    residual (bulk reductions in the L2) and for out != resid (plain bulk stores); the counters end at zero; and a
+    second call on the same counters gives the same bits (they are self-cleaning)."""
+    n = 800
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda)
+    bias = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    gamma = (1 + 0.1 * torch.randn(n, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(n, generator=g)).to(cuda)
+    x0 = torch.randn(m, n, generator=g).to(cuda)
+    a_hi, a_lo = split_ref(a)
+    w_hi, w_lo = split_ref(w)
+    sync = torch.zeros((m + 31) // 32 + 1, dtype=torch.int32, device=cuda)
+    results = []
+    launches = []
+    for flag in (1, 1, 0):
+        fact_lib.fact_set_flag(b"gemm_fuse_ln", flag)
+        x = x0.clone()
+        out = x if inplace else torch.full((m, n), float("nan"), device=cuda)
+        ln_hi = torch.zeros(m, n, dtype=torch.bfloat16, device=cuda)
+        ln_lo = torch.zeros_like(ln_hi)
+        e = _epi(kind=L.EPI_BIAS_RESID_F32, out_f32=out, ldo=n, bias=bias, resid=x, ldr=n, ln_gamma=gamma,
+                 ln_beta=beta, ln_hi=ln_hi)
+        e.ln_sync = sync.data_ptr()
+        if precise:
+            e.ln_lo = ln_lo.data_ptr()
+        n0 = fact_lib.fact_launch_count()
+        try:
+            L.check(fact_lib.fact_gemm(a_hi.data_ptr(), a_lo.data_ptr() if precise else None, k, w_hi.data_ptr(),
+                                       w_lo.data_ptr() if precise else None, k, m, n, k, C.byref(e), _st()))
+            torch.cuda.synchronize()
+        finally:
+            fact_lib.fact_set_flag(b"gemm_fuse_ln", 1)
+        launches.append(fact_lib.fact_launch_count() - n0)
+        assert int(sync.abs().sum()) == 0, "arrival counters not left at zero"
+        results.append((out.clone(), ln_hi.clone(), ln_lo.clone()))
+    assert launches == [1, 1, 2], launches
+    for other in results[1:]:
+        for t0, t1 in zip(results[0], other):
+            assert torch.equal(t0, t1)
+    out, ln_hi, ln_lo = results[0]
+    ln_ref = torch.nn.functional.layer_norm(out.double(), (n,), gamma.double(), beta.double(), 1e-5)
+    got = (join(ln_hi, ln_lo) if precise else ln_hi.float()).double()
+    assert rel_err(got, ln_ref) < (3e-5 if precise else 4e-3)
+
+
 def test_gemm_tc_inplace_residual(fact_lib, cuda):
     """out-proj / FF2 write the residual stream in place (out == resid)."""
     m, n, k = 360, 800, 800
@@ -402,6 +454,22 @@ def test_sdpa(fact_lib, cuda, batch, n, heads, dh, precise, legacy):
         fact_lib.fact_set_flag(b"sdpa_legacy", 0)
 
 
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("batch,n", [(2, 120), (1, 240), (3, 360), (2, 384), (2, 7), (40, 360)])
+def test_sdpa_wide_boxes(fact_lib, cuda, batch, n, precise):
+    """sdpa_wide = 1 (Q / K as 64-column SWIZZLE_128B + 16-column boxes) and 2 (V too, PV = N 64 + N 16 MMAs): right
+    against torch and equal to the five-narrow-boxes layout (0) -- same products accumulated in the same order."""
+    outs = []
+    for wide in (0, 1, 2):
+        fact_lib.fact_set_flag(b"sdpa_wide", wide)
+        try:
+            outs.append(_sdpa_case(fact_lib, cuda, batch, n, 10, 80, precise))
+        finally:
+            fact_lib.fact_set_flag(b"sdpa_wide", 1)
+    for o in outs[1:]:
+        assert (o - outs[0]).abs().max() <= 1e-6 * max(1.0, float(outs[0].abs().max()))
+
+
 def _sdpa_case(fact_lib, cuda, batch, n, heads, dh, precise):
     d = heads * dh
     g = torch.Generator(device="cpu").manual_seed(5)
@@ -421,6 +489,7 @@ def _sdpa_case(fact_lib, cuda, batch, n, heads, dh, precise):
     got = join(o_hi, o_lo if precise else None).double()
     tol = 5e-5 if precise else 2e-2   # bf16 mode rounds p and the output to 8 bits
     assert (got - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), float((got - ref).abs().max())
+    return got
 
 
 @pytest.mark.parametrize("batch,n_tok,d", [(3, 12, 64), (10, 120, 800)])

@@ -197,6 +197,28 @@ def test_full_size_batch_invariance_and_determinism(cuda, fact_lib):
     assert (small - out[:2]).abs().max() <= 3e-5 * out[:2].abs().max()
 
 
+@pytest.mark.parametrize("mode", ["precise", "bf16"])
+def test_layernorm_inside_the_gemm_launch_is_bitwise_neutral(cuda, fact_lib, mode):
+    """Batch 32 (CTA-pair GEMMs): the forward with the LayerNorm done by the residual GEMMs' own warps
+    (gemm_fuse_ln = 1, the default) equals, bit for bit, the forward with a LayerNorm launch after each of them, and it
+    launches 29 kernels fewer (every out-projection, and every FF2 that is followed by another layer of its stack)."""
+    m = FACTModel(make_config(), is_training=False, mode=mode, seed=5)
+    g = torch.Generator().manual_seed(6)
+    x = {"motion_input": 0.5 * torch.randn(32, 120, 225, generator=g), "audio_input": torch.randn(32, 240, 35, generator=g)}
+    outs, counts = [], []
+    for flag in (1, 0):
+        fact_lib.fact_set_flag(b"gemm_fuse_ln", flag)
+        try:
+            n0 = fact_lib.fact_launch_count()
+            outs.append(m(x).clone())
+            counts.append(fact_lib.fact_launch_count() - n0)
+        finally:
+            fact_lib.fact_set_flag(b"gemm_fuse_ln", 1)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    assert counts[1] - counts[0] == 29, counts
+
+
 def test_full_size_ar_frames_feed_back(cuda, fact_lib):
     """Batch 128, 3 frames: frame i is row 0 of a plain forward on the window shifted by i (fact_model.py:123-131)."""
     dims = oracle_dims()
