@@ -285,7 +285,7 @@ def kernel_rooflines(model, batch, mode, peaks, stream):
              ("gemm_ff2", gemm(a_ff, w["ff2"], M, d, ff, e_ff2), 2.0 * M * d * ff)]
     # the residual GEMMs as the model calls them: LayerNorm of the finished rows inside the launch (LayerNorm warps)
     gam, bet = torch.ones(d, device=dev), torch.zeros(d, device=dev)
-    ln_sync = torch.zeros(M // 32 + 2, dtype=torch.int32, device=dev)
+    ln_sync = torch.zeros(2 * (M // 32 + 2), dtype=torch.int32, device=dev)
     e_o_ln = L.GemmEpilogue(kind=L.EPI_BIAS_RESID_F32, out_f32=x.data_ptr(), ldo=d, bias=bias_d.data_ptr(),
                             resid=x.data_ptr(), ldr=d, ln_gamma=gam.data_ptr(), ln_beta=bet.data_ptr(),
                             ln_hi=out_d[0].data_ptr(), ln_lo=lo(out_d), ln_sync=ln_sync.data_ptr())

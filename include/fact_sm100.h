@@ -187,7 +187,7 @@ typedef struct fact_gemm_epilogue {
   const float* ln_beta;
   void* ln_hi;
   void* ln_lo;
-  /* optional with ln_hi: (m + 31) / 32 ints, zero before the first call and left zero by every call.  With it, large
+  /* optional with ln_hi: 2 * ((m + 31) / 32 + 1) ints, zero before the first call and left zero by every call.  With it, large
    * problems (CTA-pair path, n a multiple of 160) normalise their rows INSIDE the GEMM launch: dedicated warps wait
    * until all column tiles of a 32-row group have landed (arrival counters in ln_sync) and write the bf16 hi / lo
    * rows while the tensor pipe works on the next tiles -- no LayerNorm launch, no second HBM read of the residual

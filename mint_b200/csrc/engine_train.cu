@@ -119,7 +119,7 @@ static size_t carve_train(const fact_dims* dm, int batch, void* base, TrainWs* w
   w.ea_x = reinterpret_cast<bf16*>(take(Ma * w.ea_kp * 2));
   w.em_w = reinterpret_cast<bf16*>(take(d * w.em_kp * 2));
   w.ea_w = reinterpret_cast<bf16*>(take(d * w.ea_kp * 2));
-  w.ln_sync_bytes = ((Mc + 31) / 32 + 1) * sizeof(int);
+  w.ln_sync_bytes = 2 * ((Mc + 31) / 32 + 1) * sizeof(int);
   w.ln_sync = reinterpret_cast<int*>(take(w.ln_sync_bytes));
   if (ws) *ws = w;
   return off;

@@ -40,6 +40,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
 int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes);
 int make_tmap_box(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes, int box_rows,
                   int box_cols);
+// bf16 [batches, rows, cols] (row pitch ld elements, dense over the batches) as a 3-D map {cols, rows, batches} with a
+// {box_cols, box_rows, 1} box, no swizzle: bulk stores of a row block that are clipped at the end of ITS clip
+int make_tmap_rows3d(CUtensorMap* out, const void* ptr, int batches, int rows, int cols, int ld, int box_rows,
+                     int box_cols);
 int num_sms();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

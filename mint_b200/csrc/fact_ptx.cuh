@@ -249,6 +249,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -370,6 +377,11 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem
                "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // global[box] += shared[box] (fp32), done by the L2: the in-place residual add without reading x into the SM
 __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -400,7 +412,8 @@ __device__ __forceinline__ void ln_row_load(const float* __restrict__ xrow, int 
     v[i] = idx < nv ? (CG ? __ldcg(xr + idx) : __ldg(xr + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-template <bool NORM>
+// GB_LDG = false: gamma / beta are read with plain loads (a shared-memory copy)
+template <bool NORM, bool GB_LDG = true>
 __device__ __forceinline__ void ln_row_finish(const float4* v, const float* __restrict__ gamma,
                                               const float* __restrict__ beta, bf16* __restrict__ hi_row,
                                               bf16* __restrict__ lo_row, int d, int lane) {
@@ -435,7 +448,7 @@ __device__ __forceinline__ void ln_row_finish(const float4* v, const float* __re
     if (idx < nv) {
       float4 y = v[i];
       if (NORM) {
-        const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
+        const float4 gg = GB_LDG ? __ldg(g4 + idx) : g4[idx], bb = GB_LDG ? __ldg(b4 + idx) : b4[idx];
         y.x = (y.x - mean) * rstd * gg.x + bb.x;
         y.y = (y.y - mean) * rstd * gg.y + bb.y;
         y.z = (y.z - mean) * rstd * gg.z + bb.z;
@@ -451,9 +464,9 @@ __device__ __forceinline__ void ln_row_finish(const float4* v, const float* __re
     }
   }
 }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 

@@ -683,6 +683,8 @@ struct Gemm2Cfg {
                                    : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static constexpr int LN_GB_OFF = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;  // LNW: gamma | beta, fp32 [1024] each
+  static constexpr int SMEM_BYTES_LN = SMEM_BYTES + 2 * 1024 * 4;
   static_assert(STAGE_BYTES % 1024 == 0, "staging boxes need the 1024-byte alignment the stages keep");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=256 / 32-column epilogue chunks");
   static_assert((BN / 2) % 8 == 0, "W half must be whole 8-row swizzle atoms");
@@ -792,14 +794,15 @@ __device__ __forceinline__ void epilogue_compute(const float* v, int row, int co
   }
 }
 
-// LNW (BIAS_RESID_F32 through the bulk-store epilogue only): four more warps per CTA normalise the finished rows.
+// LNW (BIAS_RESID_F32 through the bulk-store epilogue only): eight more warps per CTA normalise the finished rows.
 // A residual-stream row is complete when the tiles_n column tiles of its 256-row block have all landed, and those are
 // handled by tiles_n different clusters: every epilogue warp counts its 32-row group in ep.ln_sync once its bulk stores
-// / reductions of a tile have completed, and the LayerNorm warps of the CTA that owns column tile 0 wait for the count
-// (2 warps x tiles_n), then read the rows back from the L2 and write LayerNorm(row) split into bf16 hi / lo -- the A
-// operand of the next GEMM -- while the MMA and epilogue warps are already on their next tiles.  Same arithmetic as
+// / reductions of a tile have completed, and the LayerNorm warps that own rows of the group wait for the count
+// (2 warps x tiles_n), then read the rows back from the L2 (one row in flight behind the one being normalised; gamma
+// and beta sit in shared memory) and write LayerNorm(row) split into bf16 hi / lo -- the A operand of the next GEMM --
+// while the MMA and epilogue warps are already on their next tiles.  Same arithmetic as
 // ln_split_kernel (ln_row_finish), which this replaces: one launch and one HBM read of the residual stream fewer.
-constexpr int LN_WARPS = 4;
+constexpr int LN_WARPS = 8;
 template <int BN, int NPART, int STAGES, int EPI, bool TS, bool LNW = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS + (LNW ? LN_WARPS * 32 : 0), 1) gemm_tc2_kernel(
     const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -918,36 +921,70 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS + (LNW 
       }
     }
   } else if (LNW && warp >= 2 + EPI_WARPS) {  // ---------------- LayerNorm warps (both CTAs)
-    const int j = warp - (2 + EPI_WARPS);  // 32-row group inside this CTA's 128 rows
-    const int target = 2 * tiles_n;        // two epilogue warps (column halves) per column tile
+    // The 256 rows of a row block are dealt over the LayerNorm warps of ALL the clusters that work on its column
+    // tiles (tiles_n clusters x 2 CTAs x LN_WARPS warps = 80 units of 3 or 4 rows at N = 800): every warp has a small
+    // job per tile instead of a long one every tiles_n-th tile, so the rows of the last tiles are normalised a few
+    // microseconds after they land (the kernel's tail) instead of a whole 128-row job later.
+    const int j = warp - (2 + EPI_WARPS);
+    const int target = 2 * tiles_n;  // two epilogue warps (column halves) per column tile
+    const int nv = N >> 2;
+    const int units = tiles_n * 2 * LN_WARPS;
+    int* done = ep.ln_sync + ((M + 31) >> 5) + 1;  // second half of ln_sync: units that are past their wait
+    auto unit_of_row = [&](int r) { return ((r + 1) * units + 2 * BM - 1) / (2 * BM) - 1; };
+    float* gb = reinterpret_cast<float*>(smem_gen + Cfg::LN_GB_OFF);
+    for (int i = j * 32 + lane; i < N; i += LN_WARPS * 32) {
+      gb[i] = __ldg(ep.ln_gamma + i);
+      gb[1024 + i] = __ldg(ep.ln_beta + i);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(LN_WARPS * 32) : "memory");
+    const float* sg = gb;
+    const float* sb = gb + 1024;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      if (tile % tiles_n != 0) continue;   // the cluster that has column tile 0 normalises the block's rows
-      const int row0 = (tile / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + j * 32;
-      if (row0 >= M) continue;
-      int* ctr = ep.ln_sync + (row0 >> 5);
+      const int base = (tile / tiles_n) * (2 * BM);
+      const int u = (tile % tiles_n) * (2 * LN_WARPS) + static_cast<int>(rank) * LN_WARPS + j;
+      const int r_lo = (u * 2 * BM) / units, r_hi = ((u + 1) * 2 * BM) / units;  // rows of the block owned by unit u
+      if (r_hi == r_lo || base + (r_lo & ~31) >= M) continue;
+      const int g_lo = r_lo >> 5, g_hi = (r_hi - 1) >> 5;
       if (lane == 0) {
-        // bounded: a GEMM launch lasts about a millisecond; a count that has not arrived after ~a second never will
-        // (a caller that handed in dirty counters, or two streams sharing them) -> fail the launch instead of hanging
-        unsigned spins = 0;
-        while (ld_acquire_gpu(ctr) < target) {
-          __nanosleep(200);
-          if (++spins > (1u << 22)) __trap();
+        for (int g = g_lo; g <= g_hi && base + g * 32 < M; ++g) {
+          const int* ctr = ep.ln_sync + ((base + g * 32) >> 5);
+          // bounded: a GEMM launch lasts about a millisecond; a count that has not arrived after ~a second never will
+          // (dirty counters, or two streams sharing them) -> fail the launch instead of hanging
+          unsigned spins = 0;
+          while (ld_relaxed_gpu(ctr) < target) {
+            __nanosleep(100);
+            if (++spins > (1u << 23)) __trap();
+          }
         }
-        *ctr = 0;  // nobody touches the counter again before the next launch
+        __threadfence();  // acquire: the rows counted above are visible to the loads below
+        // the last unit past its wait on a group clears the group's counters for the next launch
+        for (int g = g_lo; g <= g_hi && base + g * 32 < M; ++g) {
+          const int gi = (base + g * 32) >> 5;
+          const int waiters = unit_of_row(g * 32 + 31) - unit_of_row(g * 32) + 1;
+          if (atomicAdd(done + gi, 1) == waiters - 1) {
+            ep.ln_sync[gi] = 0;
+            done[gi] = 0;
+          }
+        }
       }
       __syncwarp();
-      const int nrows = min(32, M - row0), nv = N >> 2;
-      for (int r = 0; r < nrows; r += 2) {  // two rows in flight: the loads come from the L2
-        float4 v0[8], v1[8];
-        const int ra = row0 + r, rb = row0 + r + 1;
-        const bool second = r + 1 < nrows;
-        ln_row_load<true>(ep.out_f32 + static_cast<size_t>(ra) * ep.ldo, nv, lane, v0);
-        if (second) ln_row_load<true>(ep.out_f32 + static_cast<size_t>(rb) * ep.ldo, nv, lane, v1);
-        ln_row_finish<true>(v0, ep.ln_gamma, ep.ln_beta, ep.ln_hi + static_cast<size_t>(ra) * N,
-                            ep.ln_lo ? ep.ln_lo + static_cast<size_t>(ra) * N : nullptr, N, lane);
-        if (second)
-          ln_row_finish<true>(v1, ep.ln_gamma, ep.ln_beta, ep.ln_hi + static_cast<size_t>(rb) * N,
-                              ep.ln_lo ? ep.ln_lo + static_cast<size_t>(rb) * N : nullptr, N, lane);
+      const int row0 = base + r_lo;
+      const int nrows = min(r_hi - r_lo, M - row0);
+      if (nrows <= 0) continue;
+      auto xrow = [&](int r) { return ep.out_f32 + static_cast<size_t>(row0 + r) * ep.ldo; };
+      auto finish = [&](const float4* v, int r) {
+        ln_row_finish<true, false>(v, sg, sb, ep.ln_hi + static_cast<size_t>(row0 + r) * N,
+                                   ep.ln_lo ? ep.ln_lo + static_cast<size_t>(row0 + r) * N : nullptr, N, lane);
+      };
+      float4 va[8], vb[8];
+      ln_row_load<true>(xrow(0), nv, lane, va);
+      for (int r = 0; r < nrows; r += 2) {  // the next row's loads (from the L2) are in flight while this one is normalised
+        if (r + 1 < nrows) ln_row_load<true>(xrow(r + 1), nv, lane, vb);
+        finish(va, r);
+        if (r + 1 < nrows) {
+          if (r + 2 < nrows) ln_row_load<true>(xrow(r + 2), nv, lane, va);
+          finish(vb, r + 1);
+        }
       }
     }
   } else if (TS) {  // ---------------- epilogue warps, bulk-store flavour: stage a 32 x 32 box, one TMA store per box
@@ -1202,6 +1239,33 @@ int make_tmap_box(CUtensorMap* out, const void* ptr, int rows, int cols, int ld,
   cache.emplace(key, *out);
   return FACT_OK;
 }
+int make_tmap_rows3d(CUtensorMap* out, const void* ptr, int batches, int rows, int cols, int ld, int box_rows,
+                     int box_cols) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, ld, box_rows + (batches << 8), box_cols};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return FACT_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  FACT_REQUIRE(enc != nullptr, FACT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  FACT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (static_cast<long long>(ld) * 2) % 16 == 0 &&
+                   (box_cols * 2) % 16 == 0,
+               FACT_ERR_BAD_ALIGN, "bulk tensor store needs 16-byte aligned base, row pitch and box rows");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * rows};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FACT_REQUIRE(r == CUDA_SUCCESS, FACT_ERR_CUDA, "cuTensorMapEncodeTiled (3-D rows) failed (%d) batches=%d rows=%d cols=%d",
+               static_cast<int>(r), batches, rows, cols);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return FACT_OK;
+}
 // the 32 x 32 box of the GEMM epilogues
 int make_tmap_out(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int elem_bytes) {
   return make_tmap_box(out, ptr, rows, cols, ld, elem_bytes, 32, 32);
@@ -1282,17 +1346,19 @@ static int launch_cfg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
                        const OutMaps& om, int m, int n, int k, const EpiArgs& ep, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN, NPART, STAGES, TS>;
   auto kern = gemm_tc2_kernel<BN, NPART, STAGES, EPI, TS, LNW>;
+  constexpr int smem_bytes = LNW ? Cfg::SMEM_BYTES_LN : Cfg::SMEM_BYTES;
+  static_assert(smem_bytes <= 232448, "exceeds 227 KB");
   static bool attr_done = false;
   if (!attr_done) {
-    FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_done = true;
   }
   const int tiles_n = (n + BN - 1) / BN, tiles_m = (m + 2 * BM - 1) / (2 * BM);
   const int num_tiles = tiles_n * tiles_m;
   int clusters = num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  FACT_CUDA_CHECK(launch_k(kern, dim3(2 * clusters), dim3(GEMM_THREADS + (LNW ? LN_WARPS * 32 : 0)), Cfg::SMEM_BYTES, st,
-                           true, a0, a1, b0, b1, om.o0, om.o1, m, n, k, tiles_n, num_tiles, ep));
+  FACT_CUDA_CHECK(launch_k(kern, dim3(2 * clusters), dim3(GEMM_THREADS + (LNW ? LN_WARPS * 32 : 0)), smem_bytes, st, true,
+                           a0, a1, b0, b1, om.o0, om.o1, m, n, k, tiles_n, num_tiles, ep));
   FACT_LAUNCH_CHECK("gemm_tc2_kernel launch");
   return FACT_OK;
 }

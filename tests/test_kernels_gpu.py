@@ -355,7 +355,7 @@ def test_gemm_layernorm_inside_the_launch(fact_lib, cuda, m, k, inplace, precise
     x0 = torch.randn(m, n, generator=g).to(cuda)
     a_hi, a_lo = split_ref(a)
     w_hi, w_lo = split_ref(w)
-    sync = torch.zeros((m + 31) // 32 + 1, dtype=torch.int32, device=cuda)
+    sync = torch.zeros(2 * ((m + 31) // 32 + 1), dtype=torch.int32, device=cuda)
     results = []
     launches = []
     for flag in (1, 1, 0):
@@ -455,19 +455,23 @@ def test_sdpa(fact_lib, cuda, batch, n, heads, dh, precise, legacy):
 
 
 @pytest.mark.parametrize("precise", [True, False])
-@pytest.mark.parametrize("batch,n", [(2, 120), (1, 240), (3, 360), (2, 384), (2, 7), (40, 360)])
-def test_sdpa_wide_boxes(fact_lib, cuda, batch, n, precise):
-    """sdpa_wide = 1 (Q / K as 64-column SWIZZLE_128B + 16-column boxes) and 2 (V too, PV = N 64 + N 16 MMAs): right
-    against torch and equal to the five-narrow-boxes layout (0) -- same products accumulated in the same order."""
+@pytest.mark.parametrize("batch,n", [(2, 120), (1, 240), (3, 360), (2, 384), (2, 7), (40, 360), (70, 360)])
+def test_sdpa_layout_and_issue_order_variants(fact_lib, cuda, batch, n, precise):
+    """sdpa_wide = 1 (Q / K as a 64-column SWIZZLE_128B box + a 16-column box, default) vs 0 (five 16-column boxes),
+    sdpa_pipe = 1 (score MMAs of tile t + 1 interleaved with the PV MMAs of tile t) vs 0 (default): every combination
+    right against torch and equal to the others -- same products accumulated in the same order.  (70, 360) gives every
+    CTA more than one tile, two of them 15."""
     outs = []
-    for wide in (0, 1, 2):
+    for wide, pipe in ((0, 0), (1, 0), (0, 1), (1, 1)):
         fact_lib.fact_set_flag(b"sdpa_wide", wide)
+        fact_lib.fact_set_flag(b"sdpa_pipe", pipe)
         try:
             outs.append(_sdpa_case(fact_lib, cuda, batch, n, 10, 80, precise))
         finally:
             fact_lib.fact_set_flag(b"sdpa_wide", 1)
+            fact_lib.fact_set_flag(b"sdpa_pipe", 0)
     for o in outs[1:]:
-        assert (o - outs[0]).abs().max() <= 1e-6 * max(1.0, float(outs[0].abs().max()))
+        assert torch.equal(o, outs[0])
 
 
 def _sdpa_case(fact_lib, cuda, batch, n, heads, dh, precise):
