@@ -410,7 +410,7 @@ static int check_weights(const fact_dims* dm, const fact_weights* w) {
 int g_ar_prune = 1;  // fact_set_flag("ar_prune", 0): run the full last layer (A-B check of the row-0 pruning)
 int g_ar_fused = 1;  // reserved for the fused small-batch decode path (fact_set_flag("ar_fused", 0) disables it)
 extern int g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_gemm_tma_store, g_gemm_bn, g_gemm_finish_ln, g_sdpa_wide,
-    g_gemm_fuse_ln, g_sdpa_pipe;
+    g_gemm_fuse_ln;
 
 // One captured frame is valid for exactly the pointers and sizes it was captured with, so the key is EVERYTHING the
 // capture bakes in: the whole weight table (every pointer of every layer), the dims, every developer flag, the call's
@@ -581,7 +581,7 @@ extern "C" int fact_infer_auto_regressive(const fact_dims* dims, const fact_weig
   FACT_CUDA_CHECK(cudaGetDevice(&device));
   key.add(static_cast<uintptr_t>(device));
   for (int f : {g_ar_prune, g_gemm_pair, g_gemm_splitk, g_sdpa_legacy, g_dual_stream, g_gemm_tma_store, g_gemm_bn,
-                g_gemm_finish_ln, g_ar_fused, g_sdpa_wide, g_gemm_fuse_ln, g_sdpa_pipe, g_pdl})   // g_pdl stays LAST: the capture fallback below rewrites it
+                g_gemm_finish_ln, g_ar_fused, g_sdpa_wide, g_gemm_fuse_ln, g_pdl})   // g_pdl stays LAST: the capture fallback below rewrites it
     key.add(static_cast<uintptr_t>(f));
   ArSession* sess = session ? static_cast<ArSession*>(session) : &g_default_session;
   cudaGraphExec_t exec = nullptr;

@@ -276,7 +276,7 @@ extern int g_dual_stream;
 extern int g_ar_prune;
 extern int g_ar_fused;
 extern int g_sdpa_wide;
-extern int g_sdpa_pipe;
+extern int g_wgrad_order;
 extern int g_gemm_fuse_ln;
 int g_sdpa_legacy = 0;  // fact_set_flag("sdpa_legacy", 1): force the mma.sync kernel (tests / A-B timing)
 
@@ -298,7 +298,7 @@ extern "C" int fact_set_flag(const char* name, int value) {
                         {"gemm_splitk", &g_gemm_splitk},   {"gemm_pair", &g_gemm_pair},
                         {"ar_fused", &g_ar_fused},         {"pdl", &g_pdl},
                         {"sdpa_wide", &g_sdpa_wide},       {"gemm_fuse_ln", &g_gemm_fuse_ln},
-                        {"sdpa_pipe", &g_sdpa_pipe}};
+                        {"wgrad_order", &g_wgrad_order}};
   for (const Flag& f : flags)
     if (name && strcmp(name, f.name) == 0) {
       *f.slot = value;

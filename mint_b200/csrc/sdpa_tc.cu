@@ -49,7 +49,7 @@ struct SdpaTcCfg {
 
 constexpr int TC_WIDE_BYTES = TC_KB * 128;  // the [128 rows][64 el] SWIZZLE_128B box of a wide operand part (16 KB)
 
-template <int NPART, int WIDE, bool PIPE>
+template <int NPART, int WIDE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
@@ -117,12 +117,11 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     b = bh / H;
   };
 
-  // Order of the key / value blocks through the shared-memory ring (producer and issuer walk the same sequence).
-  // PIPE = false: per tile K_0..K_n, V_0..V_n -- the score MMAs of a tile start when its predecessor's PV MMAs are done.
-  // PIPE = true: the score MMA of block c of tile t + 1 is issued right after the PV MMA of block c of tile t (whose P_c
-  // it overwrites -- tcgen05 MMAs of one thread execute in order), so the scores of the next tile are complete when the
-  // softmax warps get there and the tensor pipe works through their pass instead of idling:
-  //   K(0,0..n) | V(t,0) K(t+1,0) V(t,1) K(t+1,1) ... V(t,n) K(t+1,n) | ...      (Q(t+1) travels after V(t,0))
+  // Key / value blocks travel through the shared-memory ring per tile as K_0..K_n, V_0..V_n.  (Issuing the score MMA
+  // of block c of tile t + 1 right behind the PV MMA of block c of tile t -- it overwrites P_c, and MMAs of one thread
+  // execute in order -- was built and measured: 234 us instead of 223 at batch 128.  The softmax warps are what a
+  // tile waits for, and score MMAs that run during their pass compete with them for TMEM; in this order the score MMAs
+  // of the next tile overlap the output epilogue instead.)
   const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
   auto tile_of = [&](int t) { return static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x); };
 
@@ -163,25 +162,10 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         load_block(kv_smem(s), kv_full(s), which * D + h * TC_DH, b * N + c * TC_KB, which == 1 && WIDE >= 1);
         ++it;
       };
-      if (PIPE) {
-        if (my_tiles > 0) {
-          load_q(0);
-          for (int c = 0; c < nblk; ++c) load_kv(0, 1, c);
-        }
-        for (int t = 0; t < my_tiles; ++t) {
-          const bool more = t + 1 < my_tiles;
-          for (int c = 0; c < nblk; ++c) {
-            load_kv(t, 2, c);
-            if (more && c == 0) load_q(t + 1);  // the Q buffer is free once the last score MMA of tile t has read it
-            if (more) load_kv(t + 1, 1, c);
-          }
-        }
-      } else {
-        for (int t = 0; t < my_tiles; ++t) {
-          load_q(t);
-          for (int which = 1; which <= 2; ++which)      // all K blocks, then all V blocks
-            for (int c = 0; c < nblk; ++c) load_kv(t, which, c);
-        }
+      for (int t = 0; t < my_tiles; ++t) {
+        load_q(t);
+        for (int which = 1; which <= 2; ++which)      // all K blocks, then all V blocks
+          for (int c = 0; c < nblk; ++c) load_kv(t, which, c);
       }
     }
   } else if (warp == 1) {
@@ -257,21 +241,9 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         __syncwarp();
         ++it;
       };
-      if (PIPE) {
-        if (my_tiles > 0)
-          for (int c = 0; c < nblk; ++c) issue_s(0, c);
-        for (int t = 0; t < my_tiles; ++t) {
-          const bool more = t + 1 < my_tiles;
-          for (int c = 0; c < nblk; ++c) {
-            issue_pv(t, c);
-            if (more) issue_s(t + 1, c);  // overwrites P_c of tile t: in order behind the PV MMAs that read it
-          }
-        }
-      } else {
-        for (int t = 0; t < my_tiles; ++t) {
-          for (int c = 0; c < nblk; ++c) issue_s(t, c);
-          for (int c = 0; c < nblk; ++c) issue_pv(t, c);
-        }
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int c = 0; c < nblk; ++c) issue_s(t, c);
+        for (int c = 0; c < nblk; ++c) issue_pv(t, c);
       }
     }
   } else {  // ------------------------------------------------------------------------ softmax + output warps 2..9
@@ -370,13 +342,12 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (lse && half == 0 && row < N) lse[(static_cast<size_t>(b) * H + h) * N + row] = mx + log2f(lsum);
-      uint32_t hh[TC_OC / 2], ll[TC_OC / 2];
+      uint32_t hh[TC_OC / 2];
 #pragma unroll
       for (int i = 0; i < TC_OC / 2; ++i) {
-        const float x0 = ov[2 * i] * inv, x1 = ov[2 * i + 1] * inv;
-        const uint32_t hp = cvt_bf16x2(x0, x1);
-        hh[i] = hp;
-        ll[i] = cvt_bf16x2(x0 - __uint_as_float(hp << 16), x1 - __uint_as_float(hp & 0xffff0000u));
+        ov[2 * i] *= inv;
+        ov[2 * i + 1] *= inv;
+        hh[i] = cvt_bf16x2(ov[2 * i], ov[2 * i + 1]);
       }
       const uint32_t srow = stg + lane * (TC_OC * 2);
       const int c0 = h * TC_DH + half * TC_OC, r0 = qb * TC_QB + q * 32;
@@ -391,6 +362,11 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         bulk_commit_group();
       }
       if (NPART == 2) {
+        // the lo halves are computed while the engine reads the hi box out of the staging slot
+        uint32_t ll[TC_OC / 2];
+#pragma unroll
+        for (int i = 0; i < TC_OC / 2; ++i)
+          ll[i] = cvt_bf16x2(ov[2 * i] - __uint_as_float(hh[i] << 16), ov[2 * i + 1] - __uint_as_float(hh[i] & 0xffff0000u));
         if (lane == 0) bulk_wait_group_read0();
         __syncwarp();
 #pragma unroll
@@ -419,16 +395,11 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 // SWIZZLE_128B box + a 16-column box.  (V the same way, with the PV product split into an N = 64 and an N = 16 MMA, was
 // measured too: 220 vs 221 us at batch 128 -- not kept.)
 int g_sdpa_wide = 1;
-// fact_set_flag("sdpa_pipe", 1): score MMAs of tile t + 1 interleaved with the PV MMAs of tile t.  Measured SLOWER at
-// batch 128 (234 vs 223 us): the softmax warps are bound by the TMEM read port (64 B/clk), and score MMAs that run
-// during their pass take TMEM bandwidth from them; in the default order the score MMAs overlap the output epilogue.
-int g_sdpa_pipe = 0;
-
-template <int NPART, int WIDE, bool PIPE>
+template <int NPART, int WIDE>
 static int launch_sdpa_tc(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, int batch, int n,
                           int heads, int q_rows, cudaStream_t st) {
   using Cfg = SdpaTcCfg<NPART>;
-  auto kern = sdpa_tc_kernel<NPART, WIDE, PIPE>;
+  auto kern = sdpa_tc_kernel<NPART, WIDE>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     FACT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -471,15 +442,11 @@ int sdpa_tc_try(const bf16* qh, const bf16* ql, bf16* oh, bf16* ol, float* lse, 
   if ((reinterpret_cast<uintptr_t>(qh) | reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ql) |
        reinterpret_cast<uintptr_t>(ol)) & 15)
     return FACT_ERR_UNSUPPORTED;
-#define FACT_SDPA_TC(W, P)                                                                   \
-  return ql ? launch_sdpa_tc<2, W, P>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)      \
-            : launch_sdpa_tc<1, W, P>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)
-  if (g_sdpa_pipe) {
-    if (g_sdpa_wide) { FACT_SDPA_TC(1, true); }
-    FACT_SDPA_TC(0, true);
-  }
-  if (g_sdpa_wide) { FACT_SDPA_TC(1, false); }
-  FACT_SDPA_TC(0, false);
+#define FACT_SDPA_TC(W)                                                                   \
+  return ql ? launch_sdpa_tc<2, W>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)      \
+            : launch_sdpa_tc<1, W>(qh, ql, oh, ol, lse, batch, n, heads, q_rows, st)
+  if (g_sdpa_wide) { FACT_SDPA_TC(1); }
+  FACT_SDPA_TC(0);
 #undef FACT_SDPA_TC
 }
 

@@ -36,7 +36,7 @@ static_assert(W2_SMEM_BYTES <= 232448, "exceeds 227 KB");
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_wgrad2_kernel(
     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
     const __grid_constant__ CUtensorMap tmW, int MDIM, int NDIM, int NT, int swapped, int tiles_out, int num_items,
-    int splits, int num_kb, int kb_per) {
+    int splits, int num_kb, int kb_per, int tiles, int slice_major) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -77,8 +77,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
   const uint32_t tmem_base = *tmem_ptr_gen;
   auto sA = [&](int s) { return smem_base + s * W2_STAGE_BYTES; };
   auto sB = [&](int s) { return smem_base + s * W2_STAGE_BYTES + 2 * W2_BOX_BYTES; };
+  // slice_major: item = slice * tiles + tile -- the clusters that run side by side work on the SAME token slice of
+  // different tiles, so the X / dY panels of that slice are fetched from HBM once and then hit in the L2 (each X block
+  // is wanted by tiles_out tiles, each dY block by tiles / tiles_out).  Tile-major order (item = tile * splits + slice)
+  // had concurrent clusters on different token ranges: 3.4x the algorithmic bytes came from DRAM (ncu, round 1).
+  auto tile_of = [&](int item) { return slice_major ? item % tiles : item / splits; };
   auto item_kb = [&](int item, int& kb0) {
-    kb0 = (item % splits) * kb_per;
+    kb0 = (slice_major ? item / tiles : item % splits) * kb_per;
     const int kb1 = min(kb0 + kb_per, num_kb);
     return kb1 - kb0;  // >= 1 by construction of splits / kb_per
   };
@@ -87,7 +92,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
     // ---------------- TMA producer (both CTAs)
     uint32_t it = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
-      const int tile = item / splits;
+      const int tile = tile_of(item);
       const int m0 = (tile / tiles_out) * 256 + rank * 128;       // this CTA's rows of the M side
       const int n0 = (tile % tiles_out) * NT + rank * (NT >> 1);  // this CTA's half of the tile's N-side columns
       int kb0;
@@ -143,7 +148,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
     const uint32_t stg = staging_base + static_cast<uint32_t>(warp - 2) * 4096;
     uint32_t t = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++t) {
-      const int tile = item / splits;
+      const int tile = tile_of(item);
       const int row0 = (tile / tiles_out) * 256 + rank * 128 + q * 32;
       const int n0 = (tile % tiles_out) * NT;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
@@ -211,6 +216,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1) gemm_
 // fact_set_flag("wgrad_pair", v): 0 keeps the 1-SM 128 x 128 kernel (A/B timing, tests), 1 = pair kernel with the cheaper
 // orientation, 2 / 3 force the plain / transposed orientation (tests)
 int g_wgrad_pair = 1;
+// fact_set_flag("wgrad_order", 0): tile-major work items (A/B timing of the L2 reuse the slice-major order buys)
+int g_wgrad_order = 1;
 
 // returns FACT_OK and sets *done when the pair kernel took the problem; *done = false -> caller uses the 1-SM kernel
 int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, float* dW, int ldw, int tokens, int in_dim,
@@ -265,7 +272,7 @@ int wgrad_gemm_pair(const void* x_bf16, int ldx, const void* dy_bf16, int ldy, f
   const int clusters = num_items < clusters_max ? num_items : clusters_max;
   gemm_wgrad2_kernel<<<2 * clusters, W2_THREADS, W2_SMEM_BYTES, st>>>(swapped ? tmy : tmx, swapped ? tmx : tmy, tmw, m_dim,
                                                                       n_dim, nt, swapped, tiles_out, num_items, splits,
-                                                                      num_kb, kb_per);
+                                                                      num_kb, kb_per, tiles, g_wgrad_order);
   FACT_LAUNCH_CHECK("gemm_wgrad2_kernel launch");
   *done = true;
   return FACT_OK;
