@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--train-batch", dest="train_batch", type=int, default=128,
                     help="clips per GPU of the training leg (BASELINE.json configs[2]/[3])")
     ap.add_argument("--no-train", action="store_true", help="skip the data-parallel training leg")
-    ap.add_argument("--dp-overlap", dest="dp_overlap", default="auto", choices=["auto", "fused", "adam", "backward", "none"],
+    ap.add_argument("--dp-overlap", dest="dp_overlap", default="auto",
+                    choices=["auto", "fused", "fused_tail", "adam", "backward", "none"],
                     help="how the training leg hides its gradient all-reduce (mint_b200/trainer.py)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1->512 sweep leg (configs[4])")
     ap.add_argument("--sweep", default="1,2,4,8,16,32,64,128,256,512", help="clips per GPU of the sweep leg")
@@ -381,8 +382,9 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
                       "parallelism": f"dp{world}: one logical all-reduce of the flat fp32 gradient bucket per step, "
                                      "see allreduce_overlap: 'fused' = no all-reduce, ONE kernel sums the replicas' "
                                      "gradients over NVLink peer memory, applies Adam to this rank's shard and stores "
-                                     "the new weights into every replica; 'adam' / 'backward' / 'none' = NCCL all-reduce "
-                                     "in slices hidden behind the optimizer pass / the backward / not at all"
+                                     "the new weights into every replica, launched per slice of the bucket under the "
+                                     "backward ('fused_tail': once, after it); 'adam' / 'backward' / 'none' = NCCL "
+                                     "all-reduce in slices hidden behind the optimizer pass / the backward / not at all"
                                      if world > 1 else "single GPU"}}
     with torch.cuda.stream(stream):
         batch_d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -423,9 +425,9 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
             # meet-only step and compared with their mean
             modes = {}
             sync_runs = [timed(lambda: synced.train_step(batch_d), K)[0]]
-            for mode in (["fused"] if dp.arena is not None else []) + ["none", "adam", "backward"]:
+            for mode in (["fused", "fused_tail"] if dp.arena is not None else []) + ["none", "adam", "backward"]:
                 tr = dp if mode == dp.overlap else SingleTaskTrainer([], "target", model, optimizer=opt, overlap=mode,
-                                                                      arena=dp.arena if mode == "fused" else None)
+                                                                      arena=dp.arena if mode.startswith("fused") else None)
                 for _ in range(2):
                     tr.train_step(batch_d)
                 m_ms, _, _, _ = timed(lambda: tr.train_step(batch_d), K)
@@ -487,11 +489,12 @@ def run_train_leg(args, cfg, dev, world, rank, local, peaks, stream, barrier, ma
         "allreduce_overlap": dp.overlap if world > 1 else None,
         "allreduce_calibration_ms": dp.calibration_ms,
         "fused_step": ({"kernel": "dp_adam_kernel (gradient sum + Adam + weight broadcast over peer memory)",
-                        "multicast": dp.arena.mc_ptr is not None, "arena_mb": dp.arena.nbytes / 1e6}
+                        "multicast": dp.arena.mc_ptr is not None, "arena_mb": dp.arena.nbytes / 1e6,
+                        "slices_mb": [round(c * 4 / 1e6, 1) for _, c, _ in dp._plan] if dp._plan else None}
                        if dp.arena is not None else {"unavailable": dp.fused_error}) if world > 1 else None,
         "allreduce_slices_mb": ([round(c * 4 / 1e6, 1) for _, c, _ in dp._plan] if dp._plan else
                                 [round(c * 4 / 1e6, 1) for _, c in dp.even_slices()])
-        if world > 1 and dp.overlap != "fused" else None,
+        if world > 1 and not dp.overlap.startswith("fused") else None,
         "allreduce_busbw_gbs": (model.flat_gradients.numel() * 4 * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9
                                 if ar_ms else None),
         "gpu_topology": gpu_topology(world) if rank == 0 else None,

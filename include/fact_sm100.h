@@ -322,6 +322,18 @@ FACT_API int fact_dp_adam_step(void* const* peer_base, void* mc_base, long long 
                                long long wb_off, float* m, float* v, long long n, int rank, int world, float lr,
                                float beta1, float beta2, float eps, long long step, float grad_scale, void* stream);
 
+/* The same on elements [off, off + count) of the bucket only (off, count multiples of 4): this rank updates
+ * off + [rank * per, (rank + 1) * per), per = ceil(count / world) rounded up to a multiple of 8.  A data-parallel host
+ * calls it once per slice of the bucket as the backward finishes the slices (fact_train_step's stage events), on a
+ * side stream, with a cross-replica barrier in front of every call: the slice's gradient sum, update and broadcast run
+ * UNDER the rest of the backward -- which no longer reads that slice's weights -- and only the last slice is exposed.
+ * max_blocks > 0 caps the grid (a small grid shares the SMs with the backward's persistent GEMMs instead of taking
+ * them); 0 = as many blocks as the range needs. */
+FACT_API int fact_dp_adam_range(void* const* peer_base, void* mc_base, long long grad_off, long long w_off,
+                                long long wb_off, float* m, float* v, long long off, long long count, int rank,
+                                int world, float lr, float beta1, float beta2, float eps, long long step,
+                                float grad_scale, int max_blocks, void* stream);
+
 /* *out = sum g^2 (for clip_by_global_norm, single_task_trainer.py:180-183). */
 FACT_API int fact_sum_squares(const float* g, long long n, float* out, void* stream);
 

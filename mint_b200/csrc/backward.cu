@@ -1041,31 +1041,35 @@ extern "C" int fact_adam_step(float* w, const float* g, float* m, float* v, long
   return FACT_OK;
 }
 
-extern "C" int fact_dp_adam_step(void* const* peer_base, void* mc_base, long long grad_off, long long w_off,
-                                 long long wb_off, float* m, float* v, long long n, int rank, int world, float lr,
-                                 float beta1, float beta2, float eps, long long step, float grad_scale, void* stream) {
-  FACT_REQUIRE(peer_base && m && v && n > 0 && step >= 1, FACT_ERR_BAD_SHAPE, "fact_dp_adam_step: bad arguments");
+extern "C" int fact_dp_adam_range(void* const* peer_base, void* mc_base, long long grad_off, long long w_off,
+                                  long long wb_off, float* m, float* v, long long off, long long count, int rank,
+                                  int world, float lr, float beta1, float beta2, float eps, long long step,
+                                  float grad_scale, int max_blocks, void* stream) {
+  FACT_REQUIRE(peer_base && m && v && off >= 0 && count > 0 && step >= 1, FACT_ERR_BAD_SHAPE,
+               "fact_dp_adam_range: bad arguments");
   FACT_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, FACT_ERR_BAD_SHAPE,
-               "fact_dp_adam_step: rank %d of %d (at most %d replicas)", rank, world, DP_MAX_WORLD);
-  FACT_REQUIRE(grad_off % 16 == 0 && w_off % 16 == 0 && wb_off % 16 == 0 && n % 4 == 0, FACT_ERR_BAD_ALIGN,
-               "fact_dp_adam_step: offsets must be 16-byte aligned and n a multiple of 4");
+               "fact_dp_adam_range: rank %d of %d (at most %d replicas)", rank, world, DP_MAX_WORLD);
+  FACT_REQUIRE(grad_off % 16 == 0 && w_off % 16 == 0 && wb_off % 16 == 0 && off % 4 == 0 && count % 4 == 0,
+               FACT_ERR_BAD_ALIGN, "fact_dp_adam_range: byte offsets must be 16-byte aligned, off and count multiples of 4");
   DpPeers peers{};
   for (int p = 0; p < world; ++p) {
     FACT_REQUIRE(peer_base[p] != nullptr && (reinterpret_cast<uintptr_t>(peer_base[p]) & 15) == 0, FACT_ERR_BAD_ALIGN,
-                 "fact_dp_adam_step: arena of rank %d is null or misaligned", p);
+                 "fact_dp_adam_range: arena of rank %d is null or misaligned", p);
     peers.base[p] = static_cast<char*>(peer_base[p]);
   }
-  // shard r = elements [r * per, min(n, (r + 1) * per)), per a multiple of 8 (16-byte bf16 stores)
-  long long per = (n + world - 1) / world;
+  // shard r of the range = elements off + [r * per, min(count, (r + 1) * per)), per a multiple of 8
+  long long per = (count + world - 1) / world;
   per = (per + 7) / 8 * 8;
-  const long long lo = per * rank < n ? per * rank : n, hi = lo + per < n ? lo + per : n;
+  const long long lo = off + (per * rank < count ? per * rank : count);
+  const long long hi = lo + per < off + count ? lo + per : off + count;
   if (hi <= lo) return FACT_OK;
   const double t = static_cast<double>(step);
   const float lr_t = static_cast<float>(lr * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
                                         (1.0 - pow(static_cast<double>(beta1), t)));
   const long long threads = (hi - lo) / 4;
   long long blocks = (threads + 255) / 256;
-  const int grid = static_cast<int>(blocks > 4096 ? 4096 : blocks);
+  const long long cap = max_blocks > 0 ? max_blocks : 4096;
+  const int grid = static_cast<int>(blocks > cap ? cap : blocks);
   if (mc_base)
     dp_adam_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(peers, static_cast<char*>(mc_base), grad_off, w_off, wb_off,
                                                               m, v, lo, hi, rank, world, lr_t, beta1, beta2, eps,
@@ -1075,6 +1079,13 @@ extern "C" int fact_dp_adam_step(void* const* peer_base, void* mc_base, long lon
                                                                world, lr_t, beta1, beta2, eps, grad_scale);
   FACT_LAUNCH_CHECK("dp_adam_kernel");
   return FACT_OK;
+}
+
+extern "C" int fact_dp_adam_step(void* const* peer_base, void* mc_base, long long grad_off, long long w_off,
+                                 long long wb_off, float* m, float* v, long long n, int rank, int world, float lr,
+                                 float beta1, float beta2, float eps, long long step, float grad_scale, void* stream) {
+  return fact_dp_adam_range(peer_base, mc_base, grad_off, w_off, wb_off, m, v, 0, n, rank, world, lr, beta1, beta2, eps,
+                            step, grad_scale, 0, stream);
 }
 
 extern "C" int fact_sum_squares(const float* g, long long n, float* out, void* stream) {

@@ -15,6 +15,8 @@ SIGNATURES: dict = {
     "fact_cast_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "fact_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _ll, _f, _vp, _vp]),
     "fact_dp_adam_step": (_i, [C.POINTER(_vp), _vp, _ll, _ll, _ll, _vp, _vp, _ll, _i, _i, _f, _f, _f, _f, _ll, _f, _vp]),
+    "fact_dp_adam_range": (_i, [C.POINTER(_vp), _vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _i, _i, _f, _f, _f, _f, _ll, _f,
+                                _i, _vp]),
     "fact_sum_squares": (_i, [_vp, _ll, _vp, _vp]),
     "fact_train_workspace_bytes": (C.c_size_t, [_vp, _i]),
     "fact_clip_scale": (_i, [_vp, _ll, _vp, _f, _vp]),

@@ -109,6 +109,7 @@ class Adam:
         import ctypes as C
         self.begin_step()
         self._sharded = arena
+        self.__dict__.pop("_shard_ranges", None)     # whole-bucket shards from here on
         with torch.cuda.device(self.model.device):
             st = torch.cuda.current_stream(self.model.device).cuda_stream
             lib.check(self._lib.fact_dp_adam_step(
@@ -116,10 +117,30 @@ class Adam:
                 self.v.data_ptr(), arena.numel, arena.rank, arena.world, self._lr, self.beta_1, self.beta_2,
                 self.epsilon, self.iterations, float(grad_scale), st), "fact_dp_adam_step")
 
+    def dp_fused_range(self, arena, offset: int, count: int, max_blocks: int = 0, grad_scale: float = 1.0) -> None:
+        """The fused step on elements [offset, offset + count) of the bucket (fact_dp_adam_range): the data-parallel
+        trainer calls it per slice, on a side stream, as the backward finishes the slices.  begin_step() first, a
+        cross-replica barrier before every call, one after the last, then end_step().  This rank's m / v are meaningful
+        inside its shard of every slice it has been called with."""
+        self._sharded = arena
+        per = (-(-count // arena.world) + 7) // 8 * 8
+        lo = offset + min(per * arena.rank, count)
+        hi = min(lo + per, offset + count)
+        ranges = self.__dict__.setdefault("_shard_ranges", {})
+        ranges[(offset, count)] = (lo, max(hi - lo, 0))
+        with torch.cuda.device(self.model.device):
+            st = torch.cuda.current_stream(self.model.device).cuda_stream
+            lib.check(self._lib.fact_dp_adam_range(
+                arena.peer_ptrs, arena.mc_ptr, arena.grad_off, arena.w_off, arena.wb_off, self.m.data_ptr(),
+                self.v.data_ptr(), offset, count, arena.rank, arena.world, self._lr, self.beta_1, self.beta_2,
+                self.epsilon, self.iterations, float(grad_scale), int(max_blocks), st), "fact_dp_adam_range")
+
     def _mask_to_shard(self, t: torch.Tensor) -> torch.Tensor:
-        lo, cnt = self._sharded.shard()
         out = torch.zeros_like(t)
-        out[lo:lo + cnt] = t[lo:lo + cnt]
+        ranges = getattr(self, "_shard_ranges", None)
+        spans = list(ranges.values()) if ranges else [self._sharded.shard()]
+        for lo, cnt in spans:
+            out[lo:lo + cnt] = t[lo:lo + cnt]
         return out
 
     def state_dict(self):

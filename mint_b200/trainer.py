@@ -8,10 +8,18 @@ How the cross-replica sum happens is chosen by `overlap`:
 
   "fused"     (default wherever torch symmetric memory can map the replicas' buffers into each other: NVLink /
               NVSwitch boxes).  No all-reduce at all: the gradient sum, the Adam update and the mirroring of the new
-              weights are ONE hand-written kernel over peer memory (fact_dp_adam_step: each rank reduces and updates a
+              weights are ONE hand-written kernel over peer memory (fact_dp_adam_range: each rank reduces and updates a
               1/world shard -- one multimem.ld_reduce through the NVSwitch multicast per 16 bytes, or P2P loads -- and
-              stores the new fp32 / bf16 weights into every replica), bracketed by two device-side barriers.  The
-              optimizer moments are sharded (each rank keeps its shard only; Adam.state_dict() reassembles them).
+              stores the new fp32 / bf16 weights into every replica).  It runs PER SLICE of the bucket, on a side
+              stream, as the backward finishes the slices (fact_train_step's stage events; a device-side barrier over
+              the replicas in front of every slice): a slice's weights are no longer read by the rest of the backward,
+              so its sum + update + broadcast hide under the layers below and only the last slice (the audio
+              encoder's first layer and embedding) is exposed.  The slice kernels use a small grid (one block per SM at
+              most), which shares the SMs with the backward's persistent GEMMs instead of displacing their CTAs -- the
+              reason overlapping NCCL with the backward did not pay.  With gradient clipping (the norm of the whole
+              gradient is needed first) the step is one launch behind the backward ("fused_tail").  The optimizer
+              moments are sharded (each rank keeps its shards only; Adam.state_dict() reassembles them).
+  "fused_tail" the same kernel once on the whole bucket after the backward, bracketed by two barriers (A/B timing).
 
 Otherwise the sum is ONE logical NCCL all-reduce of the model's flat gradient bucket, issued as a few contiguous slices,
 hidden in one of two ways ("auto" times one all-reduce of the bucket at construction):
@@ -60,22 +68,24 @@ class SingleTaskTrainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.allreduce = allreduce
         self.chunks = max(1, int(allreduce_chunks))
-        if overlap not in ("auto", "fused", "adam", "backward", "none"):
-            raise ValueError("overlap must be auto, fused, adam, backward or none")
+        if overlap not in ("auto", "fused", "fused_tail", "adam", "backward", "none"):
+            raise ValueError("overlap must be auto, fused, fused_tail, adam, backward or none")
         staged_ok = hasattr(model, "gradient_stages")
         sliced_ok = hasattr(optimizer, "apply_range")
         self.calibration_ms = None
         self.sync_only = bool(sync_only) and not allreduce
         self._sync_word = None
         self.arena, self.fused_error = arena, None
-        if overlap in ("auto", "fused") and self.world > 1 and allreduce and hasattr(model, "adopt_symmetric") \
-                and hasattr(optimizer, "dp_fused_step"):
+        if overlap in ("auto", "fused", "fused_tail") and self.world > 1 and allreduce \
+                and hasattr(model, "adopt_symmetric") and hasattr(optimizer, "dp_fused_step"):
             if self.arena is None:
                 self.arena, self.fused_error = _make_arena(model)
-            if self.arena is not None:
+            if self.arena is not None and overlap == "auto":
                 overlap = "fused"
-        if overlap == "fused" and self.arena is None:
+        if overlap in ("fused", "fused_tail") and self.arena is None:
             overlap = "auto"                                   # symmetric memory unavailable: NCCL paths below
+        if overlap == "fused" and not (staged_ok and hasattr(optimizer, "dp_fused_range")):
+            overlap = "fused_tail"
         if overlap == "auto":
             overlap = "adam" if sliced_ok else ("backward" if staged_ok else "none")
             if self.world > 1 and allreduce and staged_ok and sliced_ok:
@@ -91,9 +101,11 @@ class SingleTaskTrainer:
         self._comm = None
         self._events = None
         self._sumsq = None
-        self._plan = plan_allreduce(model.gradient_stages(), self.chunks) if overlap == "backward" else None
+        staged_modes = ("backward", "fused")
+        self._plan = plan_allreduce(model.gradient_stages(), 2 * self.chunks if overlap == "fused" else self.chunks) \
+            if overlap in staged_modes else None
         dev = getattr(model, "device", torch.device("cpu"))
-        if self.world > 1 and overlap == "backward" and dev.type == "cuda":
+        if self.world > 1 and overlap in staged_modes and dev.type == "cuda":
             self._comm = torch.cuda.Stream(dev)
             wanted = {ev for _, _, ev in self._plan[:-1]}
             self._events = [torch.cuda.Event() if i in wanted else None
@@ -134,13 +146,30 @@ class SingleTaskTrainer:
         target = inputs.pop(self.label_key)                                     # :145
         clip = self.grad_clip_norm > 0
         reduce = self.world > 1 and self.allreduce
-        staged = reduce and self.overlap == "backward" and not clip
+        staged = reduce and self.overlap in ("backward", "fused") and not clip
         kw = {"stage_events": self._events} if staged and self._events else {}
         loss = self.model.forward_backward(inputs, target, loss_scale=1.0 / self.world, **kw)   # :151-158, 178
         grads = self.model.flat_gradients
         if clip:                                                                # :180-183, per replica, before the sum
             clip_by_global_norm_(self.model, self.grad_clip_norm, self)
-        if reduce and self.overlap == "fused":                                  # :186-187 + Adam + re-mirroring, fused
+        if reduce and self.overlap == "fused" and staged and self._comm is not None:
+            # :186-187 + Adam + re-mirroring, fused, slice by slice under the backward (module docstring)
+            cur = torch.cuda.current_stream(grads.device)
+            self.optimizer.begin_step()
+            sms = torch.cuda.get_device_properties(grads.device).multi_processor_count
+            with torch.cuda.stream(self._comm):
+                for off, cnt, ev in self._plan[:-1]:
+                    self._comm.wait_event(self._events[ev])
+                    self.arena.barrier()            # every replica has finished this slice (and with its weights)
+                    self.optimizer.dp_fused_range(self.arena, off, cnt, max_blocks=sms)
+                self._comm.wait_stream(cur)         # the last slice: behind the whole backward
+                off, cnt, _ = self._plan[-1]
+                self.arena.barrier()
+                self.optimizer.dp_fused_range(self.arena, off, cnt)
+                self.arena.barrier()                # every replica's stores into my weights have landed
+            cur.wait_stream(self._comm)
+            self.optimizer.end_step()
+        elif reduce and self.overlap in ("fused", "fused_tail"):
             self.arena.barrier()                    # every replica's gradients are final
             self.optimizer.dp_fused_step(self.arena)
             self.arena.barrier()                    # every replica's stores into my weights have landed

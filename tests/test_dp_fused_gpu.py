@@ -27,13 +27,14 @@ def _worker(rank, world, port, q):
         from tests.helpers import make_config, oracle_dims
         dims = oracle_dims(audio_dim=35, **SMALL)
         out = {"rank": rank}
-        for force_p2p in (False, True):
+        # "fused": per slice of the bucket, on a side stream, under the backward; "fused_tail": once, behind it
+        for force_p2p, mode in ((False, "fused"), (True, "fused"), (False, "fused_tail")):
             fused_m = FACTModel(make_config(**SMALL), is_training=True, mode="bf16", seed=11, device=dev)
             ref_m = FACTModel(make_config(**SMALL), is_training=True, mode="bf16", seed=11, device=dev)
             fused_o, ref_o = Adam(fused_m, learning_rate=2e-3), Adam(ref_m, learning_rate=2e-3)
-            fused_t = SingleTaskTrainer([], "target", fused_m, optimizer=fused_o, overlap="fused")
+            fused_t = SingleTaskTrainer([], "target", fused_m, optimizer=fused_o, overlap=mode)
             ref_t = SingleTaskTrainer([], "target", ref_m, optimizer=ref_o, overlap="none")
-            if fused_t.overlap != "fused":
+            if fused_t.overlap != mode:
                 out["skip"] = f"symmetric memory unavailable: {fused_t.fused_error}"
                 break
             out["multicast"] = fused_t.arena.mc_ptr is not None
@@ -61,7 +62,8 @@ def _worker(rank, world, port, q):
                     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
                     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
                     assert torch.equal(hi, lo), "replicas diverged"
-            key = "p2p" if force_p2p else "default"
+            key = "p2p" if force_p2p else ("default" if mode == "fused" else "tail")
+            out[key + "_slices"] = len(fused_t._plan) if fused_t._plan else 0
             out[key + "_worst_rel"] = worst
             sd = fused_o.state_dict()                                       # collective: reassembles the shards
             out[key + "_m_rel"] = float((sd["m"].double() - ref_o.m.double()).abs().max() /
@@ -97,7 +99,8 @@ def test_fused_dp_step_matches_allreduce_then_adam(fact_lib):
         pytest.skip(results[0].get("skip") or results[1].get("skip"))
     print(results)
     for r in results:
-        for key in ("default", "p2p"):
+        for key in ("default", "p2p", "tail"):
             assert r[key + "_worst_rel"] < 2e-6, r           # same sums up to the order of two addends
             assert r[key + "_m_rel"] < 1e-5, r
             assert r[key + "_iter"] == 3
+        assert r["default_slices"] > 1 and r["tail_slices"] == 0, r
