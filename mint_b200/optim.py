@@ -57,6 +57,16 @@ def learning_rate_from_config(train_config):
     raise ValueError("Learning_rate %s not supported." % kind)
 
 
+def shard_of_range(offset: int, count: int, rank: int, world: int) -> tuple[int, int]:
+    """(first element, element count) of the piece of bucket range [offset, offset + count) that `rank` of `world`
+    updates in fact_dp_adam_range: the range is cut into pieces of ceil(count / world) rounded up to a multiple of 8
+    elements (16-byte bf16 stores); the last ranks may get a short or an empty piece.  Same arithmetic as the C side."""
+    per = (-(-count // world) + 7) // 8 * 8
+    lo = offset + min(per * rank, count)
+    hi = min(lo + per, offset + count)
+    return lo, max(hi - lo, 0)
+
+
 class Adam:
     def __init__(self, model, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
         self.model = model
@@ -123,11 +133,8 @@ class Adam:
         cross-replica barrier before every call, one after the last, then end_step().  This rank's m / v are meaningful
         inside its shard of every slice it has been called with."""
         self._sharded = arena
-        per = (-(-count // arena.world) + 7) // 8 * 8
-        lo = offset + min(per * arena.rank, count)
-        hi = min(lo + per, offset + count)
         ranges = self.__dict__.setdefault("_shard_ranges", {})
-        ranges[(offset, count)] = (lo, max(hi - lo, 0))
+        ranges[(offset, count)] = shard_of_range(offset, count, arena.rank, arena.world)
         with torch.cuda.device(self.model.device):
             st = torch.cuda.current_stream(self.model.device).cuda_stream
             lib.check(self._lib.fact_dp_adam_range(

@@ -30,3 +30,23 @@ def test_unsupported_learning_rate_kind():
         config_util.DEFAULT_CONFIG, "train_config { learning_rate { cosine_decay_learning_rate {} } }")
     with pytest.raises(ValueError):
         learning_rate_from_config(cfg["train_config"])
+
+
+def test_shards_of_a_bucket_slice_tile_it_exactly():
+    """fact_dp_adam_range / Adam.dp_fused_range: every rank updates its piece of a slice of the gradient bucket; the
+    pieces of all ranks must tile the slice exactly (no element updated twice or never), start on 4-element boundaries
+    (16-byte fp32 loads) and be multiples of 8 except the last (16-byte bf16 stores) -- for every world size the kernel
+    accepts and for slice sizes like the ones FACTModel.gradient_stages produces (multiples of 4, from one bias vector to
+    a whole transformer layer)."""
+    from mint_b200.optim import shard_of_range
+    for world in range(1, 17):
+        for offset, count in ((0, 4), (8, 800), (1024, 180228), (4096, 7483072), (12, 120406980 // 4 * 4)):
+            pieces = [shard_of_range(offset, count, r, world) for r in range(world)]
+            pos = offset
+            for lo, cnt in pieces:
+                assert cnt >= 0 and lo % 4 == 0
+                if cnt:
+                    assert lo == pos
+                    pos += cnt
+            assert pos == offset + count
+            assert all(cnt % 8 == 0 for _, cnt in pieces[:-1] if cnt and _ + cnt != offset + count)
